@@ -1,0 +1,203 @@
+/*
+ * resco_b200.h -- C-ABI of the B200-native traffic-microsimulation backend.
+ *
+ * The reference (Pi-Star-Lab/RESCO) has no plugin API of its own; the seam it offers is the
+ * `self.sumo` attribute (resco_benchmark/multi_signal.py:44,47,134,137; traffic_signal.py:29),
+ * i.e. the TraCI/libsumo call surface listed in SURVEY.md §8(b).  Each entry point below names the
+ * TraCI call(s) it replaces.  Plain pointers and sizes only; no torch / CUDA types in signatures
+ * (streams travel as `void*`).  Every function returns 0 on success or a negative RsStatus, with a
+ * message available from rs_last_error().  One host thread per RsSim.  All device work is enqueued
+ * on the stream passed to the call; results are valid after that stream is synchronised (calls that
+ * return data through HOST pointers synchronise themselves).
+ */
+#ifndef RESCO_B200_H
+#define RESCO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RS_ABI_VERSION 1
+#define RS_N_MOVEMENTS 12   /* the 12 movement keys of signal_config.py lane_sets */
+
+typedef enum RsStatus {
+  RS_OK = 0,
+  RS_ERR_INVALID = -1,   /* bad argument / inconsistent scenario */
+  RS_ERR_CUDA = -2,      /* CUDA runtime error (message has the cudaError string) */
+  RS_ERR_NOMEM = -3,
+  RS_ERR_NODEVICE = -4,  /* no sm_100 device: the product path has NO CPU fallback */
+  RS_ERR_CAPACITY = -5
+} RsStatus;
+
+/* Flat scenario tables (host pointers, copied to the device by rs_create).  Produced by
+ * resco_b200/scenario/compiler.py from the SUMO net/route files the reference passes to
+ * `traci.start` (multi_signal.py:117-137) and from config/signal_config.py. */
+typedef struct RsScenario {
+  int32_t abi_version;
+  /* sizes */
+  int32_t n_lanes, n_edges, n_links, n_foes, n_tls, n_phases, n_state_chars, n_signals;
+  int32_t n_sig_lanes, n_mv_lanes, n_mvo, n_out, n_yellow;
+  int32_t n_vtypes, n_routes, n_route_steps, n_origins, n_trips, n_origin_routes;
+  /* lanes */
+  const float* lane_len;
+  const float* lane_vmax;
+  const int32_t* lane_edge;
+  const int32_t* lane_index;
+  const int32_t* lane_perm;
+  const int32_t* lane_internal;
+  const int32_t* lane_left;
+  const int32_t* lane_right;
+  const int32_t* lane_link_off;      /* [n_lanes+1] */
+  const float* lane_tls_dist;        /* end-of-lane -> next TLS stop line, <0: none */
+  const int32_t* lane_sig;           /* signal whose lane list holds the lane, or -1 */
+  const int32_t* lane_sig_slot;      /* position in that signal's lane list */
+  /* edges */
+  const int32_t* edge_lane0;
+  const int32_t* edge_nlanes;
+  /* links (sorted by from-lane) */
+  const int32_t* link_from;
+  const int32_t* link_to;
+  const int32_t* link_via;
+  const int32_t* link_tls;
+  const int32_t* link_tlidx;
+  const int32_t* link_state;
+  const int32_t* link_to_edge;
+  const float* link_via_len;
+  const int32_t* link_last_int;
+  const int32_t* link_cont;
+  const int32_t* link_parent;
+  const int32_t* link_foe_off;       /* [n_links+1] */
+  const int32_t* foe_link;
+  const int32_t* foe_flags;          /* 1: must yield (response), 2: conflict (foes), 4: mutual */
+  /* traffic-light programs as installed (Signal.__init__, traffic_signal.py:93-100) */
+  const int32_t* tls_phase_off;      /* [n_tls+1] into phase_* */
+  const int32_t* tls_nlinks;         /* state-string length */
+  const int32_t* tls_init_phase;
+  const int32_t* tls_init_left;      /* ticks left in the initial phase */
+  const int32_t* phase_dur;          /* [n_phases] ticks */
+  const int32_t* phase_state_off;    /* [n_phases] into state_chars */
+  const uint8_t* state_chars;
+  /* controlled signals */
+  const int32_t* sig_tls;
+  const int32_t* sig_n_green;
+  const int32_t* sig_yellow_off;     /* [n_signals+1] into yellow_idx (n_green*n_green each) */
+  const int32_t* yellow_idx;         /* yellow_dict["i_j"] or -1 (traffic_signal.py:7-24) */
+  const int32_t* sig_lane_off;       /* [n_signals+1] */
+  const int32_t* sig_lane;
+  const int32_t* mv_off;             /* [n_signals*12+1] */
+  const int32_t* mv_lane;            /* slot in the signal's lane list */
+  const int32_t* mvo_off;            /* [n_signals*12+1] */
+  const int32_t* mvo_sig;
+  const int32_t* mvo_slot;
+  const int32_t* out_off;            /* [n_signals+1] */
+  const int32_t* out_sig;
+  const int32_t* out_slot;
+  /* demand */
+  const float* vtype;                /* [n_vtypes][8]: length,minGap,accel,decel,tau,sigma,maxSpeed,speedDev */
+  const int32_t* vtype_bit;
+  const int32_t* route_off;          /* [n_routes+1] */
+  const int32_t* route_edge;
+  const int32_t* route_mask;
+  const int32_t* origin_lane;        /* [n_origins] */
+  const int32_t* origin_off;         /* [n_origins+1] into trip_* (0s when synthetic) */
+  const float* trip_depart;          /* seconds after begin, sorted within origin */
+  const int32_t* trip_route;
+  const int32_t* trip_vtype;
+  const int32_t* trip_file;          /* index in the route file (tripinfo order) */
+  /* synthetic Bernoulli-per-tick demand; used when synthetic != 0 */
+  const int32_t* origin_rate;        /* P(insert request per tick) * 2^24 */
+  const int32_t* origin_route_off;   /* [n_origins+1] into origin_route */
+  const int32_t* origin_route;
+  /* parameters */
+  int32_t synthetic;
+  int32_t synthetic_vtype;
+  int32_t step_length;               /* MultiSignal(step_length) ticks per env step */
+  int32_t yellow_length;
+  int32_t end_tick;                  /* (end_time - begin) */
+  float max_distance;                /* detector range, traffic_signal.py:238-247 */
+  float sigma_override;              /* <0: use vType sigma */
+  float speed_dev_override;          /* <0: use vType speedDev */
+  int32_t vcap;                      /* max concurrently active vehicles per instance */
+  int32_t lane_change;               /* 0 disables the lane-change decision */
+} RsScenario;
+
+/* Borrowed device pointers, valid until the next mutating call.  [N,...] row-major. */
+typedef struct RsObsView {
+  int32_t n_env, n_signals, n_sig_lanes;
+  const float* lane_queue;       /* [N, n_sig_lanes]  Signal.observe 'queue' */
+  const float* lane_approach;    /* 'approach' */
+  const float* lane_total_wait;  /* 'total_wait' */
+  const float* lane_max_wait;    /* 'max_wait' */
+  const float* lane_speed_sum;   /* sum of vehicle speeds (states.drq*) */
+  const int32_t* phase;          /* [N, n_signals]  Signal.phase */
+  const float* mplight;          /* [N, n_signals, 13]  states.mplight */
+  const float* wave;             /* [N, n_signals, 12]  states.wave */
+  const float* reward_wait;      /* [N, n_signals]  rewards.wait */
+  const float* reward_wait_norm; /* rewards.wait_norm */
+  const float* reward_pressure;  /* rewards.pressure */
+  const int32_t* sig_queue_len;  /* [N, n_signals] calc_metrics queue_lengths */
+  const int32_t* sig_max_queue;  /* calc_metrics max_queues */
+} RsObsView;
+
+/* Per-instance episode statistics (utils/readXML.py:27-77 inputs). */
+typedef struct RsStats {
+  int32_t tick;            /* simulation.getTime() - begin */
+  int32_t n_active;
+  int32_t n_inserted;
+  int32_t n_arrived;
+  int32_t n_backlog;       /* departed-time reached but not yet inserted */
+  int32_t anomalies;       /* ordering violations detected (must stay 0) */
+  float sum_delay_arrived; /* sum(timeLoss + departDelay) over finished trips */
+  float sum_delay_running; /* same over vehicles still in the net */
+  float sum_delay_pending; /* (now - depart) over not-yet-inserted trips */
+  float sum_duration_arrived;
+  float sum_wait_arrived;
+  int32_t sum_active_ticks; /* sum over ticks of n_active (for the roofline V-bar) */
+} RsStats;
+
+typedef struct RsSim RsSim;
+
+const char* rs_last_error(void);
+int rs_abi_version(void);
+
+/* traci.start(...) for n_env lock-step instances on CUDA device `device`. */
+int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, uint64_t seed, RsSim** out);
+/* traci.close() */
+int rs_destroy(RsSim* sim);
+/* MultiSignal.reset(): fresh episode state for every instance (per-instance RNG key = seed + global id).
+ * `first_env_id` is the global id of local instance 0 (multi-GPU sharding keeps results invariant). */
+int rs_reset(RsSim* sim, uint64_t seed, int64_t first_env_id, void* stream);
+/* trafficlight.setPhase(id, idx) for all instances: phase[N,S] device ptr, mask[N,S] (may be NULL) */
+int rs_set_phase(RsSim* sim, const int32_t* d_phase, const uint8_t* d_mask, void* stream);
+/* simulationStep() x n_ticks */
+int rs_tick(RsSim* sim, int32_t n_ticks, void* stream);
+/* Signal.observe + states + rewards into the internal buffers (reset-time observe). */
+int rs_observe(RsSim* sim, void* stream);
+/* MultiSignal.step fused: prep_phase -> yellow ticks -> set_phase -> green ticks -> observe.
+ * d_actions: [N,S] int32 green-phase indices on the device. */
+int rs_env_step(RsSim* sim, const int32_t* d_actions, void* stream);
+/* Same through HOST buffers (the end-to-end call): copies actions H2D, steps, copies
+ * obs/reward back; h_obs [N,S,13] mplight, h_reward [N,S] (kind: 0 wait, 1 wait_norm, 2 pressure). */
+int rs_env_step_host(RsSim* sim, const int32_t* h_actions, float* h_obs, float* h_reward, int32_t reward_kind);
+/* Batched MaxPressure / MaxWave action selection on the device (agents/maxwave.py:18-38 over
+ * states.mplight[1:] / states.wave): writes [N,S] actions.  pairs [n_pairs,2]; valid [S, n_pairs] -> action or -1 */
+int rs_policy_maxpressure(RsSim* sim, const int32_t* h_pairs, int32_t n_pairs, const int32_t* h_valid,
+                          int32_t use_wave, int32_t* d_actions_out, void* stream);
+int rs_get_obs(RsSim* sim, RsObsView* out);
+int rs_get_stats(RsSim* sim, RsStats* h_out /* [N] */);
+/* Dump one instance's vehicles to host arrays (TraCI getters of the N=1 facade; parity tests).
+ * Arrays have room for vcap entries; returns count through n_out.  lane[i] is the lane index. */
+int rs_dump_vehicles(RsSim* sim, int32_t env, int32_t* n_out, int32_t* lane, float* pos, float* speed,
+                     float* accel, float* wait, float* rwait, float* tloss, int32_t* vid, int32_t* vtype,
+                     int32_t* route, int32_t* cursor, float* sf, int32_t* depart);
+int rs_get_phases(RsSim* sim, int32_t env, int32_t* h_tls_phase /* [n_tls] */);
+int64_t rs_kernel_launches(RsSim* sim);
+/* device time (ms) of the last rs_env_step's kernels, CUDA events on the launching stream */
+int rs_last_step_ms(RsSim* sim, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RESCO_B200_H */
