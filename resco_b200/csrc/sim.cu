@@ -1,0 +1,944 @@
+// sim.cu -- env-step kernel, auxiliary kernels and the C-ABI (include/resco_b200.h).
+//
+// Build (see __graft_entry__.build):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+// There is NO CPU fallback: every entry point fails with RS_ERR_NODEVICE without a CUDA device.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "sim_kernels.cuh"
+
+namespace rs {
+
+// ------------------------------------------------------------------------------------------------
+// shared-memory carve-up (host + device agree through this struct)
+struct SmemLayout {
+  int vcap, L, n_tls, S, O, SL, n_vt;
+  size_t off_bufA, off_bufB, off_vn, off_newlane, off_newidx, off_mnext, off_arr;
+  size_t off_lane_start, off_start2, off_cnt2, off_mhead;
+  size_t off_tls_phase, off_tls_end, off_next_phase, off_origin_cur, off_origin_backlog, off_origin_cand;
+  size_t off_vt, off_hdr, off_misc, off_obs;
+  size_t total;
+};
+
+__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+__host__ __device__ inline SmemLayout make_layout(const RsScenario& sc) {
+  SmemLayout m;
+  m.vcap = sc.vcap; m.L = sc.n_lanes; m.n_tls = sc.n_tls; m.S = sc.n_signals; m.O = sc.n_origins;
+  m.SL = sc.n_sig_lanes; m.n_vt = sc.n_vtypes;
+  size_t o = 0;
+  m.off_bufA = o; o = align16(o + (size_t)kVehWords * m.vcap * 4);
+  m.off_bufB = o; o = align16(o + (size_t)kVehWords * m.vcap * 4);
+  m.off_vn = o; o = align16(o + (size_t)m.vcap * 4);
+  m.off_newlane = o; o = align16(o + (size_t)m.vcap * 2);
+  m.off_newidx = o; o = align16(o + (size_t)m.vcap * 2);
+  m.off_mnext = o; o = align16(o + (size_t)m.vcap * 2);
+  m.off_arr = o; o = align16(o + (size_t)m.vcap * 2);
+  m.off_lane_start = o; o = align16(o + (size_t)(m.L + 1) * 2);
+  m.off_start2 = o; o = align16(o + (size_t)(m.L + 1) * 2);
+  m.off_cnt2 = o; o = align16(o + (size_t)m.L * 4);
+  m.off_mhead = o; o = align16(o + (size_t)m.L * 4);
+  m.off_tls_phase = o; o = align16(o + (size_t)m.n_tls * 4);
+  m.off_tls_end = o; o = align16(o + (size_t)m.n_tls * 4);
+  m.off_next_phase = o; o = align16(o + (size_t)(m.S > 0 ? m.S : 1) * 4);
+  m.off_origin_cur = o; o = align16(o + (size_t)(m.O > 0 ? m.O : 1) * 4);
+  m.off_origin_backlog = o; o = align16(o + (size_t)(m.O > 0 ? m.O : 1) * 4);
+  m.off_origin_cand = o; o = align16(o + (size_t)(m.O > 0 ? m.O : 1) * 16);
+  m.off_vt = o; o = align16(o + (size_t)m.n_vt * 8 * 4);
+  m.off_hdr = o; o = align16(o + (size_t)kHdrInts * 4);
+  m.off_misc = o; o = align16(o + 64 * 4);
+  m.off_obs = o; o = align16(o + (size_t)(m.SL > 0 ? m.SL : 1) * 5 * 4);
+  m.total = o;
+  return m;
+}
+
+// misc slots
+enum { M_NARR = 0, M_NOK, M_NAFTER, M_WARP = 16 /* 32 ints of warp totals */ };
+
+struct OriginCand { int32_t route, vt, vid, ok_dd; };   // ok_dd: -1 not ok, else depart delay
+
+// ------------------------------------------------------------------------------------------------
+template <int BLOCK>
+__device__ void tick_body(const DevSim& D, const SmemLayout& m, unsigned char* smem, Tile& T, uint32_t*& cur,
+                          uint32_t*& oth) {
+  const RsScenario& sc = D.sc;
+  const int tid = threadIdx.x;
+  const int L = m.L;
+  float* vn = (float*)(smem + m.off_vn);
+  uint16_t* newlane = (uint16_t*)(smem + m.off_newlane);
+  uint16_t* newidx = (uint16_t*)(smem + m.off_newidx);
+  uint16_t* mnext = (uint16_t*)(smem + m.off_mnext);
+  uint16_t* arr = (uint16_t*)(smem + m.off_arr);
+  uint16_t* start2 = (uint16_t*)(smem + m.off_start2);
+  int32_t* cnt2 = (int32_t*)(smem + m.off_cnt2);
+  int32_t* mhead = (int32_t*)(smem + m.off_mhead);
+  int32_t* hdr = (int32_t*)(smem + m.off_hdr);
+  int32_t* misc = (int32_t*)(smem + m.off_misc);
+  int32_t* origin_cur = (int32_t*)(smem + m.off_origin_cur);
+  int32_t* origin_backlog = (int32_t*)(smem + m.off_origin_backlog);
+  OriginCand* cand = (OriginCand*)(smem + m.off_origin_cand);
+  const int n = hdr[H_NVEH];
+
+  // ---- S0: traffic lights (static-program countdown), per-lane counters ----
+  for (int t = tid; t < m.n_tls; t += BLOCK) {
+    int p0 = __ldg(sc.tls_phase_off + t), np = __ldg(sc.tls_phase_off + t + 1) - p0;
+    int guard = 0;
+    while (T.tick >= T.tls_end[t] && guard++ < 64) {
+      int ph = (T.tls_phase[t] + 1) % np;
+      T.tls_phase[t] = ph;
+      int d = __ldg(sc.phase_dur + p0 + ph);
+      T.tls_end[t] += d > 0 ? d : 1;
+    }
+  }
+  for (int l = tid; l < L; l += BLOCK) { cnt2[l] = lane_count(T, l); mhead[l] = -1; }
+  if (tid == 0) { misc[M_NARR] = 0; misc[M_NOK] = 0; }
+  __syncthreads();
+
+  // ---- S1: plan (reads only start-of-tick state) ----
+  for (int i = tid; i < n; i += BLOCK) {
+    float v; int tg;
+    plan_vehicle(sc, T, i, v, tg);
+    vn[i] = v; newlane[i] = (uint16_t)tg;
+  }
+  __syncthreads();
+
+  // ---- S2: move: update in place, hand-off across lanes, bucket movers by target lane ----
+  for (int i = tid; i < n; i += BLOCK) {
+    int l = v_lane(T, i);
+    int vt = v_vtype(T, i);
+    float v1 = vn[i];
+    float vmaxl = fminf(__ldg(sc.lane_vmax + l) * T.sf[i], VTT(T, vt, VT_VMAX));
+    T.speed[i] = v1;
+    uint32_t w = T.wr[i];
+    uint32_t wait = v1 < kHaltSpeed ? (w & 0xFFFFu) + 1u : 0u;
+    T.wr[i] = (w & 0xFFFF0000u) | (wait & 0xFFFFu);
+    T.tloss[i] += (vmaxl - v1) / vmaxl;
+    int lcc = v_lcc(T, i);
+    if (lcc > 0) lcc -= 1;
+    float p = T.pos[i] + v1;
+    int curl = l, cc = v_cursor(T, i);
+    int route = v_route(T, i);
+    int tg = newlane[i];
+    if (tg != l) { curl = tg; lcc = kLcCooldown; }
+    else {
+      int guard = 0;
+      while (p > __ldg(sc.lane_len + curl) && guard++ < 64) {
+        int k = choose_link(sc, curl, route, cc);
+        if (k == -1) { curl = -1; break; }
+        if (k == -2) { p = __ldg(sc.lane_len + curl); break; }
+        p -= __ldg(sc.lane_len + curl);
+        int via = __ldg(sc.link_via + k);
+        curl = via >= 0 ? via : __ldg(sc.link_to + k);
+        if (!__ldg(sc.lane_internal + curl)) cc += 1;
+      }
+    }
+    T.pos[i] = p;
+    T.rc[i] = (T.rc[i] & 0xFFFFu) | ((uint32_t)cc << 16);
+    T.meta[i] = (T.meta[i] & 0xFFFF00FFu) | ((uint32_t)lcc << 8);
+    if (curl < 0) {
+      newlane[i] = (uint16_t)kArrived;
+      atomicAdd(&cnt2[l], -1);
+      int s = atomicAdd(&misc[M_NARR], 1);
+      arr[s] = (uint16_t)i;
+    } else {
+      newlane[i] = (uint16_t)curl;
+      if (curl != l) {
+        atomicAdd(&cnt2[l], -1);
+        atomicAdd(&cnt2[curl], 1);
+        int old = atomicExch(&mhead[curl], i);
+        mnext[i] = (uint16_t)(old < 0 ? 0xFFFF : old);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- S3a: arrivals (deterministic CSR order) and insertion candidates ----
+  if (tid == 0) {
+    int na = misc[M_NARR];
+    misc[M_NAFTER] = n - na;
+    float sd = __int_as_float(hdr[H_F_DELAY_ARR]), sdur = __int_as_float(hdr[H_F_DUR_ARR]);
+    int last = -1;
+    for (int k = 0; k < na; ++k) {
+      int best = 0x7FFFFFFF;
+      for (int q = 0; q < na; ++q) { int a = arr[q]; if (a > last && a < best) best = a; }
+      last = best;
+      sd += T.tloss[best] + (float)(T.dl[best] & 0xFFFFu);
+      sdur += (float)(T.tick - (int)(T.ed[best] >> 16));
+    }
+    hdr[H_F_DELAY_ARR] = __float_as_int(sd); hdr[H_F_DUR_ARR] = __float_as_int(sdur);
+    hdr[H_NARR] += na;
+  }
+  for (int o = tid; o < m.O; o += BLOCK) {
+    int lane = __ldg(sc.origin_lane + o);
+    OriginCand c; c.ok_dd = -1; c.route = 0; c.vt = 0; c.vid = 0;
+    bool have = false;
+    int dd = 0;
+    if (sc.synthetic) {
+      uint32_t r[4];
+      rng4(T, STREAM_DEMAND, (uint32_t)o, (uint32_t)T.tick, r);
+      if ((int32_t)(r[0] >> 8) < __ldg(sc.origin_rate + o)) origin_backlog[o] += 1;
+      if (origin_backlog[o] > 0) {
+        int r0 = __ldg(sc.origin_route_off + o), nr = __ldg(sc.origin_route_off + o + 1) - r0;
+        if (nr <= 0) origin_backlog[o] = 0;
+        else {
+          rng4(T, STREAM_ROUTE, (uint32_t)o, (uint32_t)origin_cur[o], r);
+          c.route = __ldg(sc.origin_route + r0 + (int)(r[0] % (uint32_t)nr));
+          c.vt = sc.synthetic_vtype;
+          c.vid = (o << 16) | (origin_cur[o] & 0xFFFF);
+          have = true;
+        }
+      }
+    } else {
+      int ci = __ldg(sc.origin_off + o) + origin_cur[o];
+      if (ci < __ldg(sc.origin_off + o + 1) && !(__ldg(sc.trip_depart + ci) > (float)T.tick)) {
+        c.route = __ldg(sc.trip_route + ci); c.vt = __ldg(sc.trip_vtype + ci); c.vid = ci;
+        dd = T.tick - (int)__ldg(sc.trip_depart + ci);
+        have = true;
+      }
+    }
+    if (have) {
+      float len = VTT(T, c.vt, VT_LEN), mingap = VTT(T, c.vt, VT_GAP);
+      bool ok = len <= __ldg(sc.lane_len + lane);
+      if (ok) {
+        // post-move tail of the origin lane = last element of the merged (stayers + movers) order
+        int a = T.lane_start[lane], b = T.lane_start[lane + 1];
+        int ls = -1;
+        for (int i = b - 1; i >= a; --i) if (newlane[i] == lane) { ls = i; break; }
+        int tailv = ls;
+        int best = -1;   // mover with the smallest (pos, then largest idx)
+        for (int q = mhead[lane]; q >= 0; q = (mnext[q] == 0xFFFF ? -1 : (int)mnext[q]))
+          if (best < 0 || T.pos[q] < T.pos[best] || (T.pos[q] == T.pos[best] && q > best)) best = q;
+        if (best >= 0 && (ls < 0 || !(T.pos[best] > T.pos[ls]))) tailv = best;
+        if (tailv >= 0) {
+          int tvt = v_vtype(T, tailv);
+          if (T.pos[tailv] - VTT(T, tvt, VT_LEN) - len - mingap < 0.0f) ok = false;
+        }
+      }
+      if (ok) { c.ok_dd = dd; atomicAdd(&misc[M_NOK], 1); }
+    }
+    cand[o] = c;
+  }
+  __syncthreads();
+
+  // ---- S3b: capacity resolution (origin order) ----
+  {
+    const int n_after = misc[M_NAFTER], n_ok = misc[M_NOK];
+    const bool all = n_after + n_ok <= m.vcap;
+    for (int o = tid; o < m.O; o += BLOCK) {
+      if (cand[o].ok_dd < 0) continue;
+      bool acc = all;
+      if (!all) {
+        int before = 0;
+        for (int q = 0; q < o; ++q) before += cand[q].ok_dd >= 0;
+        acc = n_after + before < m.vcap;
+      }
+      if (acc) {
+        atomicAdd(&cnt2[__ldg(sc.origin_lane + o)], 1);
+        atomicAdd(&hdr[H_NINS], 1);
+      } else cand[o].ok_dd = -2;   // refused by capacity
+    }
+  }
+  __syncthreads();
+  for (int o = tid; o < m.O; o += BLOCK) {
+    if (cand[o].ok_dd >= 0) { origin_cur[o] += 1; if (sc.synthetic) origin_backlog[o] -= 1; }
+  }
+
+  // ---- S4: new lane offsets ----
+  block_prefix<BLOCK>(cnt2, start2, L, misc + M_WARP);
+
+  // ---- S5: per-lane merge: stayers keep their order, movers merge in by position ----
+  for (int l = tid; l < L; l += BLOCK) {
+    int a = T.lane_start[l], b = T.lane_start[l + 1];
+    int head = mhead[l];
+    if (a == b && head < 0) continue;
+    int w = start2[l];
+    // next mover in (pos desc, idx asc) order after (ppos, pidx)
+    float ppos = 3.0e38f; int pidx = -1;
+    auto next_mover = [&](float pp, int pi) {
+      int best = -1;
+      for (int q = head; q >= 0; q = (mnext[q] == 0xFFFF ? -1 : (int)mnext[q])) {
+        float xq = T.pos[q];
+        bool after = (xq < pp) || (xq == pp && q > pi);
+        if (!after) continue;
+        if (best < 0 || xq > T.pos[best] || (xq == T.pos[best] && q < best)) best = q;
+      }
+      return best;
+    };
+    int mv = head >= 0 ? next_mover(ppos, pidx) : -1;
+    for (int i = a; i < b; ++i) {
+      if (newlane[i] != l) continue;
+      while (mv >= 0 && T.pos[mv] > T.pos[i]) { newidx[mv] = (uint16_t)w++; mv = next_mover(T.pos[mv], mv); }
+      newidx[i] = (uint16_t)w++;
+    }
+    while (mv >= 0) { newidx[mv] = (uint16_t)w++; mv = next_mover(T.pos[mv], mv); }
+  }
+  __syncthreads();
+
+  // ---- S6: scatter into the other buffer; newcomers at the back of their origin lane ----
+  {
+    Tile U = T; tile_bind(U, oth, m.vcap);
+    for (int i = tid; i < n; i += BLOCK) {
+      uint32_t nl = newlane[i];
+      if (nl == kArrived) continue;
+      int d = newidx[i];
+      U.pos[d] = T.pos[i]; U.speed[d] = T.speed[i]; U.sf[d] = T.sf[i]; U.tloss[d] = T.tloss[i];
+      U.vid[d] = T.vid[i]; U.wr[d] = T.wr[i]; U.rc[d] = T.rc[i]; U.meta[d] = T.meta[i]; U.ed[d] = T.ed[i];
+      U.dl[d] = (T.dl[i] & 0xFFFFu) | (nl << 16);
+    }
+    for (int o = tid; o < m.O; o += BLOCK) {
+      OriginCand c = cand[o];
+      if (c.ok_dd < 0) continue;
+      int lane = __ldg(sc.origin_lane + o);
+      int d = (int)start2[lane + 1] - 1;
+      float dev = sc.speed_dev_override >= 0.0f ? sc.speed_dev_override : VTT(T, c.vt, VT_DEV);
+      U.pos[d] = VTT(T, c.vt, VT_LEN); U.speed[d] = 0.0f; U.sf[d] = speed_factor(T, c.vid, dev); U.tloss[d] = 0.0f;
+      U.vid[d] = c.vid; U.wr[d] = 0u; U.rc[d] = (uint32_t)c.route;
+      U.meta[d] = (uint32_t)c.vt | (0xFFu << 16);
+      U.ed[d] = 0xFFFEu | ((uint32_t)T.tick << 16);
+      U.dl[d] = (uint32_t)(c.ok_dd & 0xFFFF) | ((uint32_t)lane << 16);
+    }
+  }
+  __syncthreads();
+
+  // ---- S7: swap, bookkeeping ----
+  {
+    uint32_t* tmp = cur; cur = oth; oth = tmp;
+    tile_bind(T, cur, m.vcap);
+    for (int l = tid; l <= L; l += BLOCK) T.lane_start[l] = start2[l];
+    const int n2 = start2[L];
+    if (tid == 0) {
+      hdr[H_NVEH] = n2;
+      hdr[H_ACTIVE] += n2;
+      hdr[H_TICK] += 1;
+      if (sc.synthetic) {
+        float pend = __int_as_float(hdr[H_F_PENDING]);
+        for (int o = 0; o < m.O; ++o) pend += (float)origin_backlog[o];
+        hdr[H_F_PENDING] = __float_as_int(pend);
+      }
+    }
+    int anom = 0;
+    for (int i = tid; i < n2; i += BLOCK)
+      if (i > 0 && (T.dl[i] >> 16) == (T.dl[i - 1] >> 16) && T.pos[i] > T.pos[i - 1]) anom += 1;
+    if (anom) atomicAdd(&hdr[H_ANOM], anom);
+    T.tick += 1;
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Signal.observe (traffic_signal.py:189-235) + states.mplight / wave + rewards.* + calc_metrics
+template <int BLOCK>
+__device__ void observe_body(const DevSim& D, const SmemLayout& m, unsigned char* smem, Tile& T, int env) {
+  const RsScenario& sc = D.sc;
+  const int tid = threadIdx.x, lane_id = tid & 31, wid = tid >> 5, nw = BLOCK / 32;
+  int32_t* hdr = (int32_t*)(smem + m.off_hdr);
+  float* ob = (float*)(smem + m.off_obs);   // [5][SL]
+  const int SL = m.SL, S = m.S;
+  const int e = hdr[H_EPOCH];
+  const uint32_t eprev = (uint32_t)(e - 1) & 0xFFFFu;
+  for (int q = wid; q < SL; q += nw) {     // one warp per inbound lane: segmented shuffle reduction
+    int lane = __ldg(sc.sig_lane + q);
+    int sg = __ldg(sc.lane_sig + lane);
+    float tdist = __ldg(sc.lane_tls_dist + lane), llen = __ldg(sc.lane_len + lane);
+    float queue = 0, appr = 0, tw = 0, mw = 0, ss = 0;
+    int a = T.lane_start[lane], b = T.lane_start[lane + 1];
+    for (int i = a + lane_id; i < b; i += 32) {
+      if (tdist < 0.0f) continue;
+      float dist = (llen - T.pos[i]) + tdist;
+      if (!(dist <= sc.max_distance)) continue;
+      uint32_t w = T.wr[i], mt = T.meta[i], ed = T.ed[i];
+      uint32_t rwait = w >> 16, wait = w & 0xFFFFu;
+      bool contiguous = ((ed & 0xFFFFu) == eprev) && (((mt >> 16) & 0xFFu) == (uint32_t)sg) && e > 0;
+      if (!contiguous) rwait = 0;
+      if (rwait > 0) rwait += (uint32_t)sc.step_length;
+      else if (wait > 0) rwait = wait;
+      if (rwait > 0xFFFFu) rwait = 0xFFFFu;
+      T.wr[i] = wait | (rwait << 16);
+      T.meta[i] = (mt & 0xFF00FFFFu) | ((uint32_t)sg << 16);
+      T.ed[i] = (ed & 0xFFFF0000u) | ((uint32_t)e & 0xFFFFu);
+      float rw = (float)rwait;
+      if (rwait > 0) { tw += rw; queue += 1.0f; mw = fmaxf(mw, rw); } else appr += 1.0f;
+      ss += T.speed[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      queue += __shfl_xor_sync(0xffffffffu, queue, o);
+      appr += __shfl_xor_sync(0xffffffffu, appr, o);
+      tw += __shfl_xor_sync(0xffffffffu, tw, o);
+      ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o));
+    }
+    if (lane_id == 0) {
+      ob[0 * SL + q] = queue; ob[1 * SL + q] = appr; ob[2 * SL + q] = tw; ob[3 * SL + q] = mw; ob[4 * SL + q] = ss;
+      size_t g = (size_t)env * SL + q;
+      D.lane_queue[g] = queue; D.lane_approach[g] = appr; D.lane_total_wait[g] = tw;
+      D.lane_max_wait[g] = mw; D.lane_speed_sum[g] = ss;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) hdr[H_EPOCH] = e + 1;
+  for (int x = tid; x < S * 12; x += BLOCK) {
+    int sg = x / 12, mv = x % 12;
+    int q0 = __ldg(sc.sig_lane_off + sg);
+    float qsum = 0, wsum = 0;
+    for (int j = __ldg(sc.mv_off + x); j < __ldg(sc.mv_off + x + 1); ++j) {
+      int q = q0 + __ldg(sc.mv_lane + j);
+      qsum += ob[q];
+      wsum += ob[q] + ob[SL + q];
+    }
+    for (int j = __ldg(sc.mvo_off + x); j < __ldg(sc.mvo_off + x + 1); ++j)
+      qsum -= ob[__ldg(sc.sig_lane_off + __ldg(sc.mvo_sig + j)) + __ldg(sc.mvo_slot + j)];
+    D.mplight[((size_t)env * S + sg) * 13 + 1 + mv] = qsum;
+    D.wave[((size_t)env * S + sg) * 12 + mv] = wsum;
+  }
+  for (int sg = tid; sg < S; sg += BLOCK) {
+    int q0 = __ldg(sc.sig_lane_off + sg), q1 = __ldg(sc.sig_lane_off + sg + 1);
+    int ph = T.tls_phase[__ldg(sc.sig_tls + sg)];
+    float tw = 0, ql = 0, mq = 0;
+    for (int q = q0; q < q1; ++q) { tw += ob[2 * SL + q]; ql += ob[q]; mq = fmaxf(mq, ob[q]); }
+    float pr = ql;
+    for (int j = __ldg(sc.out_off + sg); j < __ldg(sc.out_off + sg + 1); ++j)
+      pr -= ob[__ldg(sc.sig_lane_off + __ldg(sc.out_sig + j)) + __ldg(sc.out_slot + j)];
+    size_t g = (size_t)env * S + sg;
+    D.phase_obs[g] = ph;
+    D.mplight[g * 13] = (float)ph;
+    D.rew_wait[g] = -tw;
+    D.rew_wait_norm[g] = fminf(fmaxf(-tw / 224.0f, -4.0f), 4.0f);
+    D.rew_pressure[g] = -pr;
+    D.sig_queue_len[g] = (int32_t)ql; D.sig_max_queue[g] = (int32_t)mq;
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dev_set_phase(const RsScenario& sc, Tile& T, int sg, int idx) {
+  int t = __ldg(sc.sig_tls + sg);
+  int p0 = __ldg(sc.tls_phase_off + t), np = __ldg(sc.tls_phase_off + t + 1) - p0;
+  if (idx < 0 || idx >= np) return;
+  T.tls_phase[t] = idx;
+  T.tls_end[t] = T.tick + __ldg(sc.phase_dur + p0 + idx);
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_run(DevSim D, RunArgs A) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const RsScenario& sc = D.sc;
+  const SmemLayout m = make_layout(sc);
+  const int env = blockIdx.x, tid = threadIdx.x;
+  uint32_t* cur = (uint32_t*)(smem + m.off_bufA);
+  uint32_t* oth = (uint32_t*)(smem + m.off_bufB);
+  int32_t* hdr = (int32_t*)(smem + m.off_hdr);
+  int32_t* next_phase = (int32_t*)(smem + m.off_next_phase);
+  int32_t* origin_cur = (int32_t*)(smem + m.off_origin_cur);
+  int32_t* origin_backlog = (int32_t*)(smem + m.off_origin_backlog);
+  float* vt = (float*)(smem + m.off_vt);
+  Tile T;
+  tile_bind(T, cur, m.vcap);
+  T.lane_start = (uint16_t*)(smem + m.off_lane_start);
+  T.tls_phase = (int32_t*)(smem + m.off_tls_phase);
+  T.tls_end = (int32_t*)(smem + m.off_tls_end);
+  T.vt = vt;
+  const uint64_t env_id = (uint64_t)(D.first_env_id + env);
+  T.env_lo = (uint32_t)env_id; T.env_hi = (uint32_t)(env_id >> 32);
+  T.seed_lo = (uint32_t)D.seed; T.seed_hi = (uint32_t)(D.seed >> 32);
+
+  // ---- stage the instance tile: HBM -> shared (128-bit coalesced loads) ----
+  if (tid < kHdrInts) hdr[tid] = D.hdr[(size_t)env * kHdrInts + tid];
+  for (int i = tid; i < m.n_tls; i += BLOCK) {
+    T.tls_phase[i] = D.tls_phase[(size_t)env * m.n_tls + i];
+    T.tls_end[i] = D.tls_end[(size_t)env * m.n_tls + i];
+  }
+  for (int i = tid; i < m.S; i += BLOCK) next_phase[i] = D.next_phase[(size_t)env * m.S + i];
+  for (int i = tid; i < m.O; i += BLOCK) {
+    origin_cur[i] = D.origin_cur[(size_t)env * m.O + i];
+    origin_backlog[i] = D.origin_backlog[(size_t)env * m.O + i];
+  }
+  for (int i = tid; i < m.n_vt * 8; i += BLOCK) vt[i] = __ldg(sc.vtype + i);
+  __syncthreads();
+  const int n0 = hdr[H_NVEH];
+  {
+    const uint32_t* g = D.veh + (size_t)env * kVehWords * m.vcap;
+    const int n4 = (n0 + 3) >> 2;
+    for (int w = 0; w < kVehWords; ++w) {
+      const uint4* src = (const uint4*)(g + (size_t)w * m.vcap);
+      uint4* dst = (uint4*)(cur + (size_t)w * m.vcap);
+      for (int i = tid; i < n4; i += BLOCK) dst[i] = __ldcs(src + i);
+    }
+  }
+  T.tick = hdr[H_TICK];
+  __syncthreads();
+  // lane offsets from the per-vehicle lane ids (vehicles are stored lane-major)
+  for (int l = tid; l <= m.L; l += BLOCK) {
+    int lo = 0, hi = n0;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if ((int)(T.dl[mid] >> 16) < l) lo = mid + 1; else hi = mid; }
+    T.lane_start[l] = (uint16_t)lo;
+  }
+  __syncthreads();
+
+  // ---- MultiSignal.step schedule (multi_signal.py:164-197) ----
+  if (A.do_prep) {
+    for (int sg = tid; sg < m.S; sg += BLOCK) {   // Signal.prep_phase (traffic_signal.py:176-184)
+      int act = A.actions[(size_t)env * m.S + sg];
+      int cp = T.tls_phase[__ldg(sc.sig_tls + sg)];
+      if (cp == act) next_phase[sg] = cp;
+      else {
+        next_phase[sg] = act;
+        int ng = __ldg(sc.sig_n_green + sg);
+        if (cp >= 0 && cp < ng && act >= 0 && act < ng) {
+          int y = __ldg(sc.yellow_idx + __ldg(sc.sig_yellow_off + sg) + cp * ng + act);
+          if (y >= 0) dev_set_phase(sc, T, sg, y);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for (int k = 0; k < A.ticks_a; ++k) tick_body<BLOCK>(D, m, smem, T, cur, oth);
+  if (A.do_set) {
+    for (int sg = tid; sg < m.S; sg += BLOCK) dev_set_phase(sc, T, sg, next_phase[sg]);
+    __syncthreads();
+  }
+  for (int k = 0; k < A.ticks_b; ++k) tick_body<BLOCK>(D, m, smem, T, cur, oth);
+  if (A.do_observe) observe_body<BLOCK>(D, m, smem, T, env);
+
+  // ---- write the tile back ----
+  {
+    const int n1 = hdr[H_NVEH];
+    uint32_t* g = D.veh + (size_t)env * kVehWords * m.vcap;
+    const int n4 = (n1 + 3) >> 2;
+    for (int w = 0; w < kVehWords; ++w) {
+      uint4* dst = (uint4*)(g + (size_t)w * m.vcap);
+      const uint4* src = (const uint4*)(cur + (size_t)w * m.vcap);
+      for (int i = tid; i < n4; i += BLOCK) __stcs(dst + i, src[i]);
+    }
+  }
+  if (tid < kHdrInts) D.hdr[(size_t)env * kHdrInts + tid] = hdr[tid];
+  for (int i = tid; i < m.n_tls; i += BLOCK) {
+    D.tls_phase[(size_t)env * m.n_tls + i] = T.tls_phase[i];
+    D.tls_end[(size_t)env * m.n_tls + i] = T.tls_end[i];
+  }
+  for (int i = tid; i < m.S; i += BLOCK) D.next_phase[(size_t)env * m.S + i] = next_phase[i];
+  for (int i = tid; i < m.O; i += BLOCK) {
+    D.origin_cur[(size_t)env * m.O + i] = origin_cur[i];
+    D.origin_backlog[(size_t)env * m.O + i] = origin_backlog[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void k_reset(DevSim D) {
+  const int env = blockIdx.x;
+  const RsScenario& sc = D.sc;
+  for (int i = threadIdx.x; i < kHdrInts; i += blockDim.x) D.hdr[(size_t)env * kHdrInts + i] = 0;
+  for (int i = threadIdx.x; i < sc.n_tls; i += blockDim.x) {
+    D.tls_phase[(size_t)env * sc.n_tls + i] = sc.tls_init_phase[i];
+    D.tls_end[(size_t)env * sc.n_tls + i] = sc.tls_init_left[i];
+  }
+  for (int i = threadIdx.x; i < sc.n_signals; i += blockDim.x) D.next_phase[(size_t)env * sc.n_signals + i] = 0;
+  for (int i = threadIdx.x; i < sc.n_origins; i += blockDim.x) {
+    D.origin_cur[(size_t)env * sc.n_origins + i] = 0;
+    D.origin_backlog[(size_t)env * sc.n_origins + i] = 0;
+  }
+}
+
+__global__ void k_set_phase(DevSim D, const int32_t* phase, const uint8_t* mask) {
+  const RsScenario& sc = D.sc;
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= D.n_env * sc.n_signals) return;
+  if (mask && !mask[x]) return;
+  int env = x / sc.n_signals, sg = x % sc.n_signals;
+  int t = sc.sig_tls[sg];
+  int p0 = sc.tls_phase_off[t], np = sc.tls_phase_off[t + 1] - p0;
+  int idx = phase[x];
+  if (idx < 0 || idx >= np) return;
+  D.tls_phase[(size_t)env * sc.n_tls + t] = idx;
+  D.tls_end[(size_t)env * sc.n_tls + t] = D.hdr[(size_t)env * kHdrInts + H_TICK] + sc.phase_dur[p0 + idx];
+}
+
+// per-instance episode statistics: sequential loops in storage order (matches the oracle's order)
+__global__ void k_stats(DevSim D, RsStats* out) {
+  int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= D.n_env) return;
+  const RsScenario& sc = D.sc;
+  const int32_t* h = D.hdr + (size_t)env * kHdrInts;
+  RsStats st;
+  st.tick = h[H_TICK]; st.n_active = h[H_NVEH]; st.n_inserted = h[H_NINS]; st.n_arrived = h[H_NARR];
+  st.anomalies = h[H_ANOM]; st.sum_active_ticks = h[H_ACTIVE];
+  st.sum_delay_arrived = __int_as_float(h[H_F_DELAY_ARR]);
+  st.sum_duration_arrived = __int_as_float(h[H_F_DUR_ARR]);
+  st.sum_wait_arrived = 0.0f;
+  const uint32_t* g = D.veh + (size_t)env * kVehWords * sc.vcap;
+  const float* tloss = (const float*)(g + 3 * (size_t)sc.vcap);
+  const uint32_t* dl = g + 9 * (size_t)sc.vcap;
+  float run = 0;
+  for (int i = 0; i < st.n_active; ++i) run += tloss[i] + (float)(dl[i] & 0xFFFFu);
+  st.sum_delay_running = run;
+  int backlog = 0;
+  if (!sc.synthetic) {
+    float pend = 0;
+    for (int o = 0; o < sc.n_origins; ++o)
+      for (int c = sc.origin_off[o] + D.origin_cur[(size_t)env * sc.n_origins + o]; c < sc.origin_off[o + 1]; ++c)
+        if (sc.trip_depart[c] <= (float)st.tick) { pend += (float)st.tick - sc.trip_depart[c]; backlog++; }
+    st.sum_delay_pending = pend;
+  } else {
+    st.sum_delay_pending = __int_as_float(h[H_F_PENDING]);
+    for (int o = 0; o < sc.n_origins; ++o) backlog += D.origin_backlog[(size_t)env * sc.n_origins + o];
+  }
+  st.n_backlog = backlog;
+  out[env] = st;
+}
+
+// Batched WaveAgent.act (agents/maxwave.py:18-38): argmax over valid phase pairs of obs[p0]+obs[p1].
+// obs = states.mplight[1:] (MAXPRESSURE, agents/maxpressure.py:13-18) or states.wave (MAXWAVE).
+__global__ void k_policy(DevSim D, const int32_t* pairs, int n_pairs, const int32_t* valid, int use_wave,
+                         int32_t* actions) {
+  const RsScenario& sc = D.sc;
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= D.n_env * sc.n_signals) return;
+  int sg = x % sc.n_signals;
+  const float* ob = use_wave ? D.wave + (size_t)x * 12 : D.mplight + (size_t)x * 13 + 1;
+  float best = 0.0f; int bi = -1;
+  for (int p = 0; p < n_pairs; ++p) {
+    int act = valid[sg * n_pairs + p];
+    if (act < 0) continue;
+    float pr = ob[pairs[2 * p]] + ob[pairs[2 * p + 1]];
+    if (bi < 0 || pr > best) { best = pr; bi = act; }
+  }
+  actions[x] = bi < 0 ? 0 : bi;
+}
+
+}  // namespace rs
+
+// ================================================================================================
+// C-ABI
+// ================================================================================================
+using namespace rs;
+
+struct RsSim {
+  DevSim d;
+  SmemLayout layout;
+  int device;
+  int block;
+  std::vector<void*> allocs;
+  int64_t launches;
+  cudaEvent_t ev0, ev1;
+  bool timed;
+  // host staging for rs_env_step_host
+  int32_t* h_act_pinned; float* h_obs_pinned; float* h_rew_pinned;
+  int32_t* d_actions;
+  RsStats* d_stats;
+  int32_t *d_pairs, *d_valid; int n_pairs_alloc;
+};
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) \
+  return fail(RS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); } while (0)
+
+extern "C" const char* rs_last_error(void) { return g_err.c_str(); }
+extern "C" int rs_abi_version(void) { return RS_ABI_VERSION; }
+
+template <typename T>
+static int dev_dup(RsSim* s, const T*& field, size_t count) {
+  size_t bytes = sizeof(T) * (count ? count : 1);
+  void* p = nullptr;
+  CK(cudaMalloc(&p, bytes));
+  s->allocs.push_back(p);
+  if (field && count) CK(cudaMemcpy(p, field, sizeof(T) * count, cudaMemcpyHostToDevice));
+  else CK(cudaMemset(p, 0, bytes));
+  field = (const T*)p;
+  return 0;
+}
+template <typename T>
+static int dev_alloc(RsSim* s, T*& out, size_t count) {
+  void* p = nullptr;
+  size_t bytes = sizeof(T) * (count ? count : 1);
+  CK(cudaMalloc(&p, bytes));
+  CK(cudaMemset(p, 0, bytes));
+  s->allocs.push_back(p);
+  out = (T*)p;
+  return 0;
+}
+#define TRY(x) do { int _r = (x); if (_r) return _r; } while (0)
+
+template <int BLOCK>
+static int launch_run(RsSim* s, const RunArgs& a, cudaStream_t st) {
+  k_run<BLOCK><<<s->d.n_env, BLOCK, s->layout.total, st>>>(s->d, a);
+  s->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static int run(RsSim* s, const RunArgs& a, cudaStream_t st) {
+  switch (s->block) {
+    case 32: return launch_run<32>(s, a, st);
+    case 64: return launch_run<64>(s, a, st);
+    case 128: return launch_run<128>(s, a, st);
+    case 256: return launch_run<256>(s, a, st);
+    default: return fail(RS_ERR_INVALID, "block size must be 32/64/128/256");
+  }
+}
+
+static int configure(RsSim* s) {
+  const int bytes = (int)s->layout.total;
+  switch (s->block) {
+    case 32: CK(cudaFuncSetAttribute(k_run<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); break;
+    case 64: CK(cudaFuncSetAttribute(k_run<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); break;
+    case 128: CK(cudaFuncSetAttribute(k_run<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); break;
+    case 256: CK(cudaFuncSetAttribute(k_run<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); break;
+    default: return fail(RS_ERR_INVALID, "RESCO_B200_BLOCK must be 32/64/128/256");
+  }
+  return 0;
+}
+
+extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, uint64_t seed, RsSim** out) {
+  if (!sc || !out || n_env <= 0) return fail(RS_ERR_INVALID, "rs_create: bad arguments");
+  if (sc->abi_version != RS_ABI_VERSION) return fail(RS_ERR_INVALID, "rs_create: ABI version mismatch");
+  if (sc->vcap <= 0 || sc->vcap % 4 || sc->vcap > 65528) return fail(RS_ERR_INVALID, "rs_create: vcap must be a positive multiple of 4 (< 65528)");
+  if (sc->n_lanes >= 65535 || sc->n_signals > 254 || sc->n_routes > 65535 || sc->n_vtypes > 255)
+    return fail(RS_ERR_INVALID, "rs_create: scenario exceeds the packed-field ranges");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return fail(RS_ERR_NODEVICE, "rs_create: no CUDA device (this backend has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(RS_ERR_INVALID, "rs_create: bad device index");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(RS_ERR_NODEVICE, "rs_create: built for sm_100a (Blackwell) only");
+  RsSim* s = new RsSim();
+  s->device = device; s->launches = 0; s->timed = false; s->n_pairs_alloc = 0;
+  s->d.sc = *sc; s->d.n_env = n_env; s->d.seed = seed; s->d.first_env_id = 0;
+  RsScenario& d = s->d.sc;
+  const int L = sc->n_lanes, K = sc->n_links, S = sc->n_signals;
+  TRY(dev_dup(s, d.lane_len, L)); TRY(dev_dup(s, d.lane_vmax, L)); TRY(dev_dup(s, d.lane_edge, L));
+  TRY(dev_dup(s, d.lane_index, L)); TRY(dev_dup(s, d.lane_perm, L)); TRY(dev_dup(s, d.lane_internal, L));
+  TRY(dev_dup(s, d.lane_left, L)); TRY(dev_dup(s, d.lane_right, L)); TRY(dev_dup(s, d.lane_link_off, L + 1));
+  TRY(dev_dup(s, d.lane_tls_dist, L)); TRY(dev_dup(s, d.lane_sig, L)); TRY(dev_dup(s, d.lane_sig_slot, L));
+  TRY(dev_dup(s, d.edge_lane0, sc->n_edges)); TRY(dev_dup(s, d.edge_nlanes, sc->n_edges));
+  TRY(dev_dup(s, d.link_from, K)); TRY(dev_dup(s, d.link_to, K)); TRY(dev_dup(s, d.link_via, K));
+  TRY(dev_dup(s, d.link_tls, K)); TRY(dev_dup(s, d.link_tlidx, K)); TRY(dev_dup(s, d.link_state, K));
+  TRY(dev_dup(s, d.link_to_edge, K)); TRY(dev_dup(s, d.link_via_len, K)); TRY(dev_dup(s, d.link_last_int, K));
+  TRY(dev_dup(s, d.link_cont, K)); TRY(dev_dup(s, d.link_parent, K)); TRY(dev_dup(s, d.link_foe_off, K + 1));
+  TRY(dev_dup(s, d.foe_link, sc->n_foes)); TRY(dev_dup(s, d.foe_flags, sc->n_foes));
+  TRY(dev_dup(s, d.tls_phase_off, sc->n_tls + 1)); TRY(dev_dup(s, d.tls_nlinks, sc->n_tls));
+  TRY(dev_dup(s, d.tls_init_phase, sc->n_tls)); TRY(dev_dup(s, d.tls_init_left, sc->n_tls));
+  TRY(dev_dup(s, d.phase_dur, sc->n_phases)); TRY(dev_dup(s, d.phase_state_off, sc->n_phases));
+  TRY(dev_dup(s, d.state_chars, sc->n_state_chars));
+  TRY(dev_dup(s, d.sig_tls, S)); TRY(dev_dup(s, d.sig_n_green, S)); TRY(dev_dup(s, d.sig_yellow_off, S + 1));
+  TRY(dev_dup(s, d.yellow_idx, sc->n_yellow)); TRY(dev_dup(s, d.sig_lane_off, S + 1));
+  TRY(dev_dup(s, d.sig_lane, sc->n_sig_lanes)); TRY(dev_dup(s, d.mv_off, S * 12 + 1));
+  TRY(dev_dup(s, d.mv_lane, sc->n_mv_lanes)); TRY(dev_dup(s, d.mvo_off, S * 12 + 1));
+  TRY(dev_dup(s, d.mvo_sig, sc->n_mvo)); TRY(dev_dup(s, d.mvo_slot, sc->n_mvo));
+  TRY(dev_dup(s, d.out_off, S + 1)); TRY(dev_dup(s, d.out_sig, sc->n_out)); TRY(dev_dup(s, d.out_slot, sc->n_out));
+  TRY(dev_dup(s, d.vtype, (size_t)sc->n_vtypes * 8)); TRY(dev_dup(s, d.vtype_bit, sc->n_vtypes));
+  TRY(dev_dup(s, d.route_off, sc->n_routes + 1)); TRY(dev_dup(s, d.route_edge, sc->n_route_steps));
+  TRY(dev_dup(s, d.route_mask, sc->n_route_steps));
+  TRY(dev_dup(s, d.origin_lane, sc->n_origins)); TRY(dev_dup(s, d.origin_off, sc->n_origins + 1));
+  TRY(dev_dup(s, d.trip_depart, sc->n_trips)); TRY(dev_dup(s, d.trip_route, sc->n_trips));
+  TRY(dev_dup(s, d.trip_vtype, sc->n_trips)); TRY(dev_dup(s, d.trip_file, sc->n_trips));
+  TRY(dev_dup(s, d.origin_rate, sc->n_origins)); TRY(dev_dup(s, d.origin_route_off, sc->n_origins + 1));
+  TRY(dev_dup(s, d.origin_route, sc->n_origin_routes));
+  const size_t N = (size_t)n_env;
+  TRY(dev_alloc(s, s->d.hdr, N * kHdrInts));
+  TRY(dev_alloc(s, s->d.tls_phase, N * sc->n_tls)); TRY(dev_alloc(s, s->d.tls_end, N * sc->n_tls));
+  TRY(dev_alloc(s, s->d.next_phase, N * S));
+  TRY(dev_alloc(s, s->d.origin_cur, N * sc->n_origins)); TRY(dev_alloc(s, s->d.origin_backlog, N * sc->n_origins));
+  TRY(dev_alloc(s, s->d.veh, N * kVehWords * sc->vcap));
+  const size_t SL = sc->n_sig_lanes;
+  TRY(dev_alloc(s, s->d.lane_queue, N * SL)); TRY(dev_alloc(s, s->d.lane_approach, N * SL));
+  TRY(dev_alloc(s, s->d.lane_total_wait, N * SL)); TRY(dev_alloc(s, s->d.lane_max_wait, N * SL));
+  TRY(dev_alloc(s, s->d.lane_speed_sum, N * SL));
+  TRY(dev_alloc(s, s->d.phase_obs, N * S)); TRY(dev_alloc(s, s->d.mplight, N * S * 13));
+  TRY(dev_alloc(s, s->d.wave, N * S * 12)); TRY(dev_alloc(s, s->d.rew_wait, N * S));
+  TRY(dev_alloc(s, s->d.rew_wait_norm, N * S)); TRY(dev_alloc(s, s->d.rew_pressure, N * S));
+  TRY(dev_alloc(s, s->d.sig_queue_len, N * S)); TRY(dev_alloc(s, s->d.sig_max_queue, N * S));
+  TRY(dev_alloc(s, s->d_actions, N * (S ? S : 1)));
+  TRY(dev_alloc(s, s->d_stats, N));
+  CK(cudaMallocHost((void**)&s->h_act_pinned, sizeof(int32_t) * N * (S ? S : 1)));
+  CK(cudaMallocHost((void**)&s->h_obs_pinned, sizeof(float) * N * (S ? S : 1) * 13));
+  CK(cudaMallocHost((void**)&s->h_rew_pinned, sizeof(float) * N * (S ? S : 1)));
+  s->layout = make_layout(s->d.sc);
+  if (s->layout.total > (size_t)prop.sharedMemPerBlockOptin) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "rs_create: instance tile needs %zu B shared memory (> %zu B per CTA); lower vcap",
+             s->layout.total, (size_t)prop.sharedMemPerBlockOptin);
+    rs_destroy(s);
+    return fail(RS_ERR_CAPACITY, buf);
+  }
+  const char* eb = getenv("RESCO_B200_BLOCK");
+  s->block = eb ? atoi(eb) : 128;
+  TRY(configure(s));
+  CK(cudaEventCreate(&s->ev0)); CK(cudaEventCreate(&s->ev1));
+  *out = s;
+  return rs_reset(s, seed, 0, nullptr);
+}
+
+extern "C" int rs_destroy(RsSim* s) {
+  if (!s) return 0;
+  cudaSetDevice(s->device);
+  for (void* p : s->allocs) cudaFree(p);
+  if (s->h_act_pinned) cudaFreeHost(s->h_act_pinned);
+  if (s->h_obs_pinned) cudaFreeHost(s->h_obs_pinned);
+  if (s->h_rew_pinned) cudaFreeHost(s->h_rew_pinned);
+  if (s->ev0) cudaEventDestroy(s->ev0);
+  if (s->ev1) cudaEventDestroy(s->ev1);
+  delete s;
+  return 0;
+}
+
+extern "C" int rs_reset(RsSim* s, uint64_t seed, int64_t first_env_id, void* stream) {
+  if (!s) return fail(RS_ERR_INVALID, "rs_reset: null sim");
+  CK(cudaSetDevice(s->device));
+  s->d.seed = seed; s->d.first_env_id = first_env_id;
+  k_reset<<<s->d.n_env, 64, 0, (cudaStream_t)stream>>>(s->d);
+  s->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int rs_set_phase(RsSim* s, const int32_t* d_phase, const uint8_t* d_mask, void* stream) {
+  if (!s || !d_phase) return fail(RS_ERR_INVALID, "rs_set_phase: bad arguments");
+  int total = s->d.n_env * s->d.sc.n_signals;
+  if (total == 0) return 0;
+  k_set_phase<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(s->d, d_phase, d_mask);
+  s->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int rs_tick(RsSim* s, int32_t n_ticks, void* stream) {
+  if (!s || n_ticks < 0) return fail(RS_ERR_INVALID, "rs_tick: bad arguments");
+  RunArgs a{nullptr, 0, n_ticks, 0, 0, 0};
+  return run(s, a, (cudaStream_t)stream);
+}
+
+extern "C" int rs_observe(RsSim* s, void* stream) {
+  if (!s) return fail(RS_ERR_INVALID, "rs_observe: null sim");
+  RunArgs a{nullptr, 0, 0, 0, 0, 1};
+  return run(s, a, (cudaStream_t)stream);
+}
+
+extern "C" int rs_env_step(RsSim* s, const int32_t* d_actions, void* stream) {
+  if (!s || !d_actions) return fail(RS_ERR_INVALID, "rs_env_step: bad arguments");
+  const RsScenario& sc = s->d.sc;
+  RunArgs a{d_actions, 1, sc.yellow_length, 1, sc.step_length - sc.yellow_length, 1};
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaEventRecord(s->ev0, st));
+  int r = run(s, a, st);
+  if (r) return r;
+  CK(cudaEventRecord(s->ev1, st));
+  s->timed = true;
+  return 0;
+}
+
+extern "C" int rs_env_step_host(RsSim* s, const int32_t* h_actions, float* h_obs, float* h_reward, int32_t reward_kind) {
+  if (!s || !h_actions) return fail(RS_ERR_INVALID, "rs_env_step_host: bad arguments");
+  const size_t NS = (size_t)s->d.n_env * s->d.sc.n_signals;
+  memcpy(s->h_act_pinned, h_actions, sizeof(int32_t) * NS);
+  CK(cudaMemcpyAsync(s->d_actions, s->h_act_pinned, sizeof(int32_t) * NS, cudaMemcpyHostToDevice, 0));
+  int r = rs_env_step(s, s->d_actions, nullptr);
+  if (r) return r;
+  const float* rew = reward_kind == 0 ? s->d.rew_wait : (reward_kind == 1 ? s->d.rew_wait_norm : s->d.rew_pressure);
+  if (h_obs) CK(cudaMemcpyAsync(s->h_obs_pinned, s->d.mplight, sizeof(float) * NS * 13, cudaMemcpyDeviceToHost, 0));
+  if (h_reward) CK(cudaMemcpyAsync(s->h_rew_pinned, rew, sizeof(float) * NS, cudaMemcpyDeviceToHost, 0));
+  CK(cudaStreamSynchronize(0));
+  if (h_obs) memcpy(h_obs, s->h_obs_pinned, sizeof(float) * NS * 13);
+  if (h_reward) memcpy(h_reward, s->h_rew_pinned, sizeof(float) * NS);
+  return 0;
+}
+
+extern "C" int rs_policy_maxpressure(RsSim* s, const int32_t* h_pairs, int32_t n_pairs, const int32_t* h_valid,
+                                     int32_t use_wave, int32_t* d_actions_out, void* stream) {
+  if (!s || !h_pairs || !h_valid || n_pairs <= 0) return fail(RS_ERR_INVALID, "rs_policy_maxpressure: bad arguments");
+  const int S = s->d.sc.n_signals;
+  if (s->n_pairs_alloc != n_pairs) {
+    TRY(dev_alloc(s, s->d_pairs, (size_t)n_pairs * 2));
+    TRY(dev_alloc(s, s->d_valid, (size_t)n_pairs * S));
+    s->n_pairs_alloc = n_pairs;
+    CK(cudaMemcpy(s->d_pairs, h_pairs, sizeof(int32_t) * n_pairs * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s->d_valid, h_valid, sizeof(int32_t) * n_pairs * S, cudaMemcpyHostToDevice));
+  }
+  int total = s->d.n_env * S;
+  int32_t* outp = d_actions_out ? d_actions_out : s->d_actions;
+  k_policy<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(s->d, s->d_pairs, n_pairs, s->d_valid, use_wave, outp);
+  s->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int rs_get_obs(RsSim* s, RsObsView* o) {
+  if (!s || !o) return fail(RS_ERR_INVALID, "rs_get_obs: bad arguments");
+  o->n_env = s->d.n_env; o->n_signals = s->d.sc.n_signals; o->n_sig_lanes = s->d.sc.n_sig_lanes;
+  o->lane_queue = s->d.lane_queue; o->lane_approach = s->d.lane_approach; o->lane_total_wait = s->d.lane_total_wait;
+  o->lane_max_wait = s->d.lane_max_wait; o->lane_speed_sum = s->d.lane_speed_sum; o->phase = s->d.phase_obs;
+  o->mplight = s->d.mplight; o->wave = s->d.wave; o->reward_wait = s->d.rew_wait;
+  o->reward_wait_norm = s->d.rew_wait_norm; o->reward_pressure = s->d.rew_pressure;
+  o->sig_queue_len = s->d.sig_queue_len; o->sig_max_queue = s->d.sig_max_queue;
+  return 0;
+}
+
+extern "C" int rs_get_stats(RsSim* s, RsStats* h_out) {
+  if (!s || !h_out) return fail(RS_ERR_INVALID, "rs_get_stats: bad arguments");
+  CK(cudaSetDevice(s->device));
+  CK(cudaDeviceSynchronize());
+  k_stats<<<(s->d.n_env + 63) / 64, 64>>>(s->d, s->d_stats);
+  s->launches += 1;
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(h_out, s->d_stats, sizeof(RsStats) * s->d.n_env, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int rs_dump_vehicles(RsSim* s, int32_t env, int32_t* n_out, int32_t* lane, float* pos, float* speed,
+                                float* accel, float* wait, float* rwait, float* tloss, int32_t* vid, int32_t* vtype,
+                                int32_t* route, int32_t* cursor, float* sf, int32_t* depart) {
+  if (!s || env < 0 || env >= s->d.n_env || !n_out) return fail(RS_ERR_INVALID, "rs_dump_vehicles: bad arguments");
+  CK(cudaSetDevice(s->device));
+  CK(cudaDeviceSynchronize());
+  const int vcap = s->d.sc.vcap;
+  int32_t hdr[kHdrInts];
+  CK(cudaMemcpy(hdr, s->d.hdr + (size_t)env * kHdrInts, sizeof hdr, cudaMemcpyDeviceToHost));
+  int n = hdr[H_NVEH];
+  std::vector<uint32_t> buf((size_t)kVehWords * vcap);
+  CK(cudaMemcpy(buf.data(), s->d.veh + (size_t)env * kVehWords * vcap, buf.size() * 4, cudaMemcpyDeviceToHost));
+  const float* fpos = (const float*)&buf[0]; const float* fspeed = (const float*)&buf[(size_t)vcap];
+  const float* fsf = (const float*)&buf[2 * (size_t)vcap]; const float* ftl = (const float*)&buf[3 * (size_t)vcap];
+  const uint32_t *wvid = &buf[4 * (size_t)vcap], *wr = &buf[5 * (size_t)vcap], *rc = &buf[6 * (size_t)vcap];
+  const uint32_t *mt = &buf[7 * (size_t)vcap], *ed = &buf[8 * (size_t)vcap], *dl = &buf[9 * (size_t)vcap];
+  for (int i = 0; i < n; ++i) {
+    if (lane) lane[i] = (int32_t)(dl[i] >> 16);
+    if (pos) pos[i] = fpos[i];
+    if (speed) speed[i] = fspeed[i];
+    if (accel) accel[i] = 0.0f;   // not part of the device state (TraCI facade differentiates speeds)
+    if (wait) wait[i] = (float)(wr[i] & 0xFFFFu);
+    if (rwait) rwait[i] = (float)(wr[i] >> 16);
+    if (tloss) tloss[i] = ftl[i];
+    if (vid) vid[i] = (int32_t)wvid[i];
+    if (vtype) vtype[i] = (int32_t)(mt[i] & 0xFFu);
+    if (route) route[i] = (int32_t)(rc[i] & 0xFFFFu);
+    if (cursor) cursor[i] = (int32_t)(rc[i] >> 16);
+    if (sf) sf[i] = fsf[i];
+    if (depart) depart[i] = (int32_t)(ed[i] >> 16);
+  }
+  *n_out = n;
+  return 0;
+}
+
+extern "C" int rs_get_phases(RsSim* s, int32_t env, int32_t* h_tls_phase) {
+  if (!s || env < 0 || env >= s->d.n_env || !h_tls_phase) return fail(RS_ERR_INVALID, "rs_get_phases: bad arguments");
+  CK(cudaSetDevice(s->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(h_tls_phase, s->d.tls_phase + (size_t)env * s->d.sc.n_tls, sizeof(int32_t) * s->d.sc.n_tls,
+                cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int64_t rs_kernel_launches(RsSim* s) { return s ? s->launches : 0; }
+
+extern "C" int rs_last_step_ms(RsSim* s, float* ms) {
+  if (!s || !ms || !s->timed) return fail(RS_ERR_INVALID, "rs_last_step_ms: no timed step");
+  CK(cudaEventSynchronize(s->ev1));
+  CK(cudaEventElapsedTime(ms, s->ev0, s->ev1));
+  return 0;
+}

@@ -1,0 +1,469 @@
+// sim_kernels.cuh -- sm_100a kernels of the lock-step traffic microsimulation.
+//
+// One CTA owns one environment instance for a whole MultiSignal.step() (multi_signal.py:164-197):
+// the instance's vehicle tile (Structure-of-Arrays, lane-major, front vehicle first) is staged
+// from HBM into shared memory once, `step_length` one-second ticks run entirely out of shared
+// memory (car-following / lane change / junction right-of-way / lane hand-off / insertion /
+// arrival), Signal.observe + states.* + rewards.* are reduced with warp shuffles, and the tile is
+// written back.  HBM traffic per env step is therefore ~1 read + 1 write of the tile instead of
+// one per tick.  No tensor cores: there is no dense contraction on this path.
+//
+// Arithmetic is plain IEEE fp32 with FMA contraction disabled (-fmad=false), the same operation
+// order as the rule set written down in DESIGN.md §4, so results are bit-identical to the CPU
+// oracle used by the tests.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/resco_b200.h"
+
+namespace rs {
+
+constexpr int kMaxHops = 8;
+constexpr float kHaltSpeed = 0.1f;
+constexpr float kNumEps = 0.001f;
+constexpr float kEmergencyDecel = 9.0f;
+constexpr int kLcCooldown = 5;
+constexpr int kVehWords = 10;      // 32-bit words per vehicle record
+constexpr int kHdrInts = 16;
+constexpr uint32_t kArrived = 0xFFFFu;
+
+// header slots (ints; floats bit-cast)
+enum { H_TICK = 0, H_NVEH, H_EPOCH, H_NINS, H_NARR, H_ANOM, H_ACTIVE, H_F_DELAY_ARR, H_F_DUR_ARR, H_F_PENDING };
+
+// vtype table columns
+enum { VT_LEN = 0, VT_GAP, VT_ACCEL, VT_DECEL, VT_TAU, VT_SIGMA, VT_VMAX, VT_DEV };
+
+// Device copy of RsScenario (device pointers) + per-sim buffers.
+struct DevSim {
+  RsScenario sc;          // pointers are DEVICE pointers
+  int32_t n_env;
+  uint64_t seed;
+  int64_t first_env_id;
+  // per-instance state in HBM
+  int32_t* hdr;           // [N][kHdrInts]
+  int32_t* tls_phase;     // [N][n_tls]
+  int32_t* tls_end;       // [N][n_tls]
+  int32_t* next_phase;    // [N][S]
+  int32_t* origin_cur;    // [N][O]
+  int32_t* origin_backlog;// [N][O]
+  uint32_t* veh;          // [N][kVehWords][vcap]
+  // observation outputs
+  float *lane_queue, *lane_approach, *lane_total_wait, *lane_max_wait, *lane_speed_sum;  // [N][SL]
+  int32_t* phase_obs;     // [N][S]
+  float *mplight, *wave, *rew_wait, *rew_wait_norm, *rew_pressure;
+  int32_t *sig_queue_len, *sig_max_queue;
+};
+
+struct RunArgs {
+  const int32_t* actions;  // [N][S] or null
+  int32_t do_prep;         // Signal.prep_phase from actions
+  int32_t ticks_a;         // ticks before set_phase
+  int32_t do_set;          // Signal.set_phase(next_phase)
+  int32_t ticks_b;         // ticks after
+  int32_t do_observe;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based RNG (Salmon et al., SC'11)
+__device__ __forceinline__ void philox(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    if (r > 0) { k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+    uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+  }
+}
+enum { STREAM_SF = 1, STREAM_DAWDLE = 2, STREAM_DEMAND = 3, STREAM_ROUTE = 4 };
+
+// ---------------------------------------------------------------------------------------------
+// car-following primitives (SUMO Euler update, dt = 1 s) -- see DESIGN.md §4.2
+__device__ __forceinline__ float brake_gap(float speed, float decel, float headway) {
+  int steps = (int)(speed / decel);
+  float fs = (float)steps;
+  float a = fs * speed;
+  float b = decel * fs;
+  float c = b * (float)(steps + 1);
+  float d = c / 2.0f;
+  return (a - d) + speed * headway;
+}
+__device__ __forceinline__ float max_safe_stop_speed(float gap, float decel, float tau) {
+  float g = gap - kNumEps;
+  if (g < 0.0f) return 0.0f;
+  float b = decel, t = tau;
+  float q = 2.0f * g / b - t;
+  float inner = 1.0f + 4.0f * (q + t * t);
+  float n = floorf(0.5f - ((t + sqrtf(inner) * -0.5f)));
+  float h = 0.5f * n * (n - 1.0f) * b + n * b * t;
+  float r = (g - h) / (n + t);
+  return n * b + r;
+}
+__device__ __forceinline__ float follow_speed(float gap, float vlead, float dlead, float decel, float tau) {
+  float bg = brake_gap(vlead, fmaxf(decel, dlead), 0.0f);
+  return max_safe_stop_speed(gap + bg, decel, tau);
+}
+__device__ __forceinline__ float free_speed(float decel, float dist, float target) {
+  if (dist < target) return target;
+  float b = decel;
+  float bb = b + 2.0f * target;
+  float y = fmaxf(0.0f, ((sqrtf(bb * bb + 8.0f * b * dist) - b) * 0.5f - target) / b);
+  float yf = floorf(y);
+  float exact = (yf * yf * b + yf * b) / 2.0f + yf * target + (y > yf ? target : 0.0f);
+  return fmaxf(0.0f, dist - exact) / (yf + 1.0f) + yf * b + target;
+}
+__device__ __forceinline__ float dawdle(float v, float accel, float sigma, float xi) {
+  if (v < accel) v -= sigma * v * xi; else v -= sigma * accel * xi;
+  return fmaxf(0.0f, v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Shared-memory view of one instance
+struct Tile {
+  // vehicle SoA (current buffer)
+  float* pos; float* speed; float* sf; float* tloss;
+  int32_t* vid;
+  uint32_t* wr;    // wait (lo16) | rwait (hi16), whole seconds
+  uint32_t* rc;    // route (lo16) | cursor (hi16)
+  uint32_t* meta;  // vtype (8) | lcc (8) | seen_sig (8, 0xFF none) | spare
+  uint32_t* ed;    // seen_epoch (lo16) | depart tick (hi16)
+  uint32_t* dl;    // depart delay (lo16) | lane (hi16)
+  uint16_t* lane_start;   // [L+1]
+  int32_t* tls_phase; int32_t* tls_end;
+  const float* vt;        // vtype table in smem
+  int32_t tick;
+  uint32_t env_lo, env_hi, seed_lo, seed_hi;
+};
+
+__device__ __forceinline__ void tile_bind(Tile& t, uint32_t* base, int vcap) {
+  t.pos = (float*)(base + 0 * vcap); t.speed = (float*)(base + 1 * vcap); t.sf = (float*)(base + 2 * vcap);
+  t.tloss = (float*)(base + 3 * vcap); t.vid = (int32_t*)(base + 4 * vcap); t.wr = base + 5 * vcap;
+  t.rc = base + 6 * vcap; t.meta = base + 7 * vcap; t.ed = base + 8 * vcap; t.dl = base + 9 * vcap;
+}
+
+#define VTT(t, i, f) ((t).vt[(i) * 8 + (f)])
+__device__ __forceinline__ int v_vtype(const Tile& t, int i) { return (int)(t.meta[i] & 0xFFu); }
+__device__ __forceinline__ int v_lcc(const Tile& t, int i) { return (int)((t.meta[i] >> 8) & 0xFFu); }
+__device__ __forceinline__ int v_route(const Tile& t, int i) { return (int)(t.rc[i] & 0xFFFFu); }
+__device__ __forceinline__ int v_cursor(const Tile& t, int i) { return (int)(t.rc[i] >> 16); }
+__device__ __forceinline__ int v_wait(const Tile& t, int i) { return (int)(t.wr[i] & 0xFFFFu); }
+__device__ __forceinline__ int v_lane(const Tile& t, int i) { return (int)(t.dl[i] >> 16); }
+__device__ __forceinline__ int lane_count(const Tile& t, int l) { return (int)t.lane_start[l + 1] - (int)t.lane_start[l]; }
+
+__device__ __forceinline__ void rng4(const Tile& t, uint32_t stream, uint32_t a, uint32_t b, uint32_t out[4]) {
+  out[0] = t.env_lo; out[1] = t.env_hi; out[2] = a; out[3] = b;
+  philox(out, t.seed_lo ^ (stream * 0x632BE5ABu), t.seed_hi);
+}
+
+__device__ __forceinline__ float speed_factor(const Tile& t, int32_t vid, float dev) {
+  if (!(dev > 0.0f)) return 1.0f;
+  uint32_t r[4];
+  rng4(t, STREAM_SF, (uint32_t)vid, 0u, r);
+  uint32_t sum = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) sum += (r[i] & 0xFFFFu) + (r[i] >> 16);
+  float z = ((float)sum - 262140.0f) * (1.0f / 65536.0f) * 1.2247449f;
+  float sf = 1.0f + dev * z;
+  return fminf(fmaxf(sf, 0.2f), 2.0f);
+}
+
+// which link does a vehicle with (route, cursor) take at the end of `lane`?  -1: route ends, -2: wrong lane
+__device__ __forceinline__ int choose_link(const RsScenario& sc, int lane, int route, int cursor) {
+  int k0 = __ldg(sc.lane_link_off + lane), k1 = __ldg(sc.lane_link_off + lane + 1);
+  if (__ldg(sc.lane_internal + lane)) return k0 < k1 ? k0 : -2;
+  int ro = __ldg(sc.route_off + route), rn = __ldg(sc.route_off + route + 1) - ro;
+  if (cursor + 1 >= rn) return -1;
+  int ne = __ldg(sc.route_edge + ro + cursor + 1), mask = __ldg(sc.route_mask + ro + cursor + 1);
+  int best = -2, rank = 0;
+  for (int k = k0; k < k1; ++k) {
+    if (__ldg(sc.link_to_edge + k) != ne) continue;
+    int ti = __ldg(sc.lane_index + __ldg(sc.link_to + k));
+    int r = ((mask >> (8 + ti)) & 1) ? 3 : (((mask >> ti) & 1) ? 2 : 1);
+    if (r > rank) { rank = r; best = k; }
+  }
+  return best;
+}
+
+__device__ __forceinline__ int state_now(const RsScenario& sc, const Tile& t, int k) {
+  int tl = __ldg(sc.link_tls + k);
+  if (tl < 0) return __ldg(sc.link_state + k);
+  int p = __ldg(sc.tls_phase_off + tl) + t.tls_phase[tl];
+  return (int)__ldg(sc.state_chars + __ldg(sc.phase_state_off + p) + __ldg(sc.link_tlidx + k));
+}
+
+__device__ __forceinline__ bool time_conflict(float seen, float v, float cross, float dist_f, float v_f, float cross_f) {
+  float vm = fmaxf(v, 4.0f), vf = fmaxf(v_f, 2.0f);
+  float tm_a = seen / vm, tm_l = (seen + cross) / vm;
+  float tf_a = dist_f / vf, tf_l = (dist_f + cross_f) / vf;
+  return (tf_a < tm_l + 1.0f) && (tf_l + 1.0f > tm_a);
+}
+
+// right-of-way: must the vehicle on entry link k wait for one of its foes?
+__device__ bool link_blocked(const RsScenario& sc, const Tile& t, int k, float seen, float v, float cross) {
+  int f0 = __ldg(sc.link_foe_off + k), f1 = __ldg(sc.link_foe_off + k + 1);
+  for (int fi = f0; fi < f1; ++fi) {
+    int f = __ldg(sc.foe_link + fi), fl = __ldg(sc.foe_flags + fi);
+    int li = __ldg(sc.link_last_int + f);
+    if (li >= 0 && lane_count(t, li) > 0) return true;   // somebody is crossing my path
+    if (!(fl & 1)) continue;                             // I have right of way over f
+    int a0 = __ldg(sc.link_from + f);
+    if (lane_count(t, a0) > 0) {
+      int h = t.lane_start[a0];
+      if (choose_link(sc, a0, v_route(t, h), v_cursor(t, h)) == f) {
+        float dist_f = __ldg(sc.lane_len + a0) - t.pos[h];
+        int fst = state_now(sc, t, f);
+        bool goes = true;
+        int hv = v_vtype(t, h);
+        if (fst == 'r' || fst == 'u' || fst == 's') goes = false;
+        else if (fst == 'y' && dist_f >= brake_gap(t.speed[h], VTT(t, hv, VT_DECEL), 0.0f)) goes = false;
+        if (t.speed[h] < kHaltSpeed) goes = false;       // a standing foe is not approaching
+        if (goes && time_conflict(seen, v, cross, dist_f, t.speed[h],
+                                  __ldg(sc.link_via_len + f) + VTT(t, hv, VT_LEN))) return true;
+      }
+    }
+    if (__ldg(sc.link_cont + f)) {
+      int a1 = __ldg(sc.link_via + f);
+      if (lane_count(t, a1) > 0) {
+        int h = t.lane_start[a1];
+        float dist_f = __ldg(sc.lane_len + a1) - t.pos[h];
+        if (t.speed[h] >= kHaltSpeed &&
+            time_conflict(seen, v, cross, dist_f, t.speed[h],
+                          __ldg(sc.link_via_len + f) - __ldg(sc.lane_len + a1) + VTT(t, v_vtype(t, h), VT_LEN)))
+          return true;
+      }
+    }
+  }
+  return false;
+}
+
+__device__ __forceinline__ float lane_occ(const Tile& t, int l) {
+  float occ = 0.0f;
+  for (int i = t.lane_start[l]; i < (int)t.lane_start[l + 1]; ++i) {
+    int vt = v_vtype(t, i);
+    occ += VTT(t, vt, VT_LEN) + VTT(t, vt, VT_GAP);
+  }
+  return occ;
+}
+
+// stop-line decision for link k, `seen` metres ahead of vehicle i (hop 0 = the link at the end of its lane)
+__device__ bool must_stop(const RsScenario& sc, const Tile& t, int i, int k, float seen, int hop, int cursor) {
+  int vt = v_vtype(t, i);
+  float len = VTT(t, vt, VT_LEN), decel = VTT(t, vt, VT_DECEL);
+  float v = t.speed[i];
+  int from = __ldg(sc.link_from + k);
+  if (__ldg(sc.lane_internal + from)) {
+    int p = __ldg(sc.link_parent + k);
+    if (hop == 0 && p >= 0 && __ldg(sc.link_cont + p) && __ldg(sc.link_via + p) == from)
+      return link_blocked(sc, t, p, seen, v, __ldg(sc.link_via_len + p) - __ldg(sc.lane_len + from) + len);
+    return false;
+  }
+  int st = state_now(sc, t, k);
+  if (st == 'r' || st == 'u') return true;
+  if (st == 'y' || st == 'Y') return seen >= brake_gap(v, decel, 0.0f);
+  if (st == 's' && !(v_wait(t, i) > 0 && seen <= 2.0f)) return true;
+  if (hop != 0) return false;
+  bool minor = (st == 'g' || st == 'm' || st == '=' || st == 'Z' || st == 'w' || st == 's' || st == 'o');
+  if (__ldg(sc.link_cont + k)) {
+    if (lane_count(t, __ldg(sc.link_via + k)) > 0) return true;   // waiting slot inside the junction is taken
+  } else if (minor) {
+    if (link_blocked(sc, t, k, seen, v, __ldg(sc.link_via_len + k) + len)) return true;
+  } else {
+    int f0 = __ldg(sc.link_foe_off + k), f1 = __ldg(sc.link_foe_off + k + 1);
+    for (int fi = f0; fi < f1; ++fi) {
+      int li = __ldg(sc.link_last_int + __ldg(sc.foe_link + fi));
+      if (li >= 0 && lane_count(t, li) > 0) return true;
+    }
+  }
+  // keep the junction clear: enter only if the vehicle fits behind whatever stands beyond it
+  float need = len + VTT(t, vt, VT_GAP), space = 0.0f;
+  int cur = __ldg(sc.link_to + k), cc2 = cursor + 1;
+  int route = v_route(t, i);
+  for (int h = 0; h < 6; ++h) {
+    float free_room = __ldg(sc.lane_len + cur) - lane_occ(t, cur);
+    if (free_room > 0.0f) space += free_room;
+    if (space >= need) return false;
+    if (lane_count(t, cur) > 0) break;
+    int k2 = choose_link(sc, cur, route, cc2);
+    if (k2 < 0) return false;
+    if (!__ldg(sc.lane_internal + cur)) {
+      int st2 = state_now(sc, t, k2);
+      if (st2 == 'r' || st2 == 'u' || st2 == 'y') break;
+    }
+    int via2 = __ldg(sc.link_via + k2);
+    cur = via2 >= 0 ? via2 : __ldg(sc.link_to + k2);
+    if (!__ldg(sc.lane_internal + cur)) cc2 += 1;
+  }
+  return space < need;
+}
+
+__device__ __forceinline__ int strategic_dir(const RsScenario& sc, int route, int cursor, int lane) {
+  int mask = __ldg(sc.route_mask + __ldg(sc.route_off + route) + cursor);
+  int okm = mask & 0xFF, bestm = (mask >> 8) & 0xFF, myidx = __ldg(sc.lane_index + lane);
+  int want = !((okm >> myidx) & 1) ? okm : (!((bestm >> myidx) & 1) ? bestm : 0);
+  if (!want) return 0;
+  for (int d = 1; d < 8; ++d) {
+    if (myidx + d < 8 && ((want >> (myidx + d)) & 1)) return 1;
+    if (myidx - d >= 0 && ((want >> (myidx - d)) & 1)) return -1;
+  }
+  return 0;
+}
+
+// Plan one vehicle from the state at the start of the tick: next speed + lane it will be in
+// laterally (own lane unless a lane change / head swap was decided).
+__device__ void plan_vehicle(const RsScenario& sc, const Tile& t, int i, float& vn_out, int& target_out) {
+  int lane = v_lane(t, i);
+  int rank = i - (int)t.lane_start[lane];
+  int vt = v_vtype(t, i);
+  float len = VTT(t, vt, VT_LEN), mingap = VTT(t, vt, VT_GAP), accel = VTT(t, vt, VT_ACCEL);
+  float decel = VTT(t, vt, VT_DECEL), tau = VTT(t, vt, VT_TAU);
+  float sigma = sc.sigma_override >= 0.0f ? sc.sigma_override : VTT(t, vt, VT_SIGMA);
+  float vcapv = VTT(t, vt, VT_VMAX);
+  float v = t.speed[i], x = t.pos[i], sf = t.sf[i];
+  int route = v_route(t, i), cursor = v_cursor(t, i);
+  float lane_len = __ldg(sc.lane_len + lane);
+  float vmaxl = fminf(__ldg(sc.lane_vmax + lane) * sf, vcapv);
+  float vacc = fminf(v + accel, vmaxl);
+  float vsafe = vacc, vlead_limit = vacc;
+  bool wrong_lane_head = false;
+  if (rank > 0) {
+    int ld = i - 1, lvt = v_vtype(t, ld);
+    float gap = t.pos[ld] - VTT(t, lvt, VT_LEN) - x - mingap;
+    vlead_limit = follow_speed(gap, t.speed[ld], VTT(t, lvt, VT_DECEL), decel, tau);
+    vsafe = fminf(vsafe, vlead_limit);
+  } else {
+    float seen = lane_len - x;
+    int cur = lane, cc = cursor;
+    float la = brake_gap(vacc, decel, 0.0f) + 2.0f * vacc + 5.0f;
+    for (int hop = 0; hop < kMaxHops; ++hop) {
+      int k = choose_link(sc, cur, route, cc);
+      if (k == -1) break;
+      if (k == -2) {
+        vsafe = fminf(vsafe, max_safe_stop_speed(seen, decel, tau));
+        if (hop == 0) wrong_lane_head = true;
+        break;
+      }
+      if (must_stop(sc, t, i, k, seen, hop, cc)) { vsafe = fminf(vsafe, max_safe_stop_speed(seen, decel, tau)); break; }
+      int via = __ldg(sc.link_via + k);
+      int nxt = via >= 0 ? via : __ldg(sc.link_to + k);
+      vsafe = fminf(vsafe, free_speed(decel, seen, fminf(__ldg(sc.lane_vmax + nxt) * sf, vcapv)));
+      if (lane_count(t, nxt) > 0) {
+        int tl = (int)t.lane_start[nxt + 1] - 1, tvt = v_vtype(t, tl);
+        float gap = seen + (t.pos[tl] - VTT(t, tvt, VT_LEN)) - mingap;
+        float f = follow_speed(gap, t.speed[tl], VTT(t, tvt, VT_DECEL), decel, tau);
+        vsafe = fminf(vsafe, f);
+        if (hop == 0) vlead_limit = fminf(vlead_limit, f);
+        break;
+      }
+      seen += __ldg(sc.lane_len + nxt);
+      if (!__ldg(sc.lane_internal + nxt)) cc += 1;
+      cur = nxt;
+      if (seen > la) break;
+    }
+  }
+  float vmin_n = fmaxf(0.0f, v - decel);
+  float vmin_e = fmaxf(0.0f, v - fmaxf(decel, kEmergencyDecel));
+  float vmin = fminf(vmin_n, fmaxf(vsafe, vmin_e));
+  float vcand = fmaxf(vmin, vsafe);
+  float vn = vcand;
+  if (sigma > 0.0f) {
+    uint32_t r[4];
+    rng4(t, STREAM_DAWDLE, (uint32_t)t.vid[i], (uint32_t)t.tick, r);
+    float xi = (float)(r[0] >> 8) * (1.0f / 16777216.0f);
+    vn = fmaxf(vmin, dawdle(vcand, accel, sigma, xi));
+  }
+  int target = -1;
+  int left = __ldg(sc.lane_left + lane), right = __ldg(sc.lane_right + lane);
+  bool internal = __ldg(sc.lane_internal + lane) != 0;
+  if (sc.lane_change && !internal && (left >= 0 || right >= 0) && x + vn <= lane_len) {
+    int mask = __ldg(sc.route_mask + __ldg(sc.route_off + route) + cursor);
+    int bestm = (mask >> 8) & 0xFF;
+    int dir = strategic_dir(sc, route, cursor, lane);
+    bool strategic = dir != 0;
+    int vbit = __ldg(sc.vtype_bit + vt);
+    for (int pass = 0; pass < 2; ++pass) {
+      int d;
+      if (strategic) { if (pass) break; d = dir; }
+      else {
+        if (v_lcc(t, i) > 0 || !(vlead_limit < vacc - 1.0f)) break;
+        d = pass == 0 ? 1 : -1;
+      }
+      if (d == 0) break;
+      if ((d > 0) == ((t.tick & 1) != 0)) continue;   // even ticks: leftward, odd ticks: rightward
+      int nl = d > 0 ? left : right;
+      if (nl < 0 || !(__ldg(sc.lane_perm + nl) & vbit)) continue;
+      if (!strategic && !((bestm >> __ldg(sc.lane_index + nl)) & 1)) continue;
+      int a = t.lane_start[nl], b = t.lane_start[nl + 1], j = a;
+      while (j < b && t.pos[j] >= x) ++j;
+      float vfol = vacc;
+      bool ok = true;
+      if (j > a) {
+        int ld = j - 1, lvt = v_vtype(t, ld);
+        float gap = t.pos[ld] - VTT(t, lvt, VT_LEN) - x - mingap;
+        if (gap < 0.0f) ok = false;
+        else {
+          vfol = follow_speed(gap, t.speed[ld], VTT(t, lvt, VT_DECEL), decel, tau);
+          if (vfol < v - decel) ok = false;
+        }
+      }
+      if (ok && j < b) {
+        int fvt = v_vtype(t, j);
+        float gap = x - len - t.pos[j] - VTT(t, fvt, VT_GAP);
+        if (gap < 0.0f) ok = false;
+        else {
+          float vf = follow_speed(gap, v, decel, VTT(t, fvt, VT_DECEL), VTT(t, fvt, VT_TAU));
+          if (vf < t.speed[j] + VTT(t, fvt, VT_ACCEL) - VTT(t, fvt, VT_DECEL)) ok = false;
+        }
+      }
+      if (!ok) continue;
+      if (!strategic && !(fminf(vfol, vacc) > vlead_limit + 1.0f)) continue;
+      target = nl;
+      vn = fmaxf(0.0f, fminf(vn, vfol));
+      break;
+    }
+  }
+  // deadlock breaker: two standing lane heads that each need the other's lane trade places
+  if (target < 0 && wrong_lane_head && sc.lane_change && v < kHaltSpeed && lane_len - x < 1.0f) {
+    int d = strategic_dir(sc, route, cursor, lane);
+    int nl = d > 0 ? left : (d < 0 ? right : -1);
+    if (nl >= 0 && lane_count(t, nl) > 0 && (__ldg(sc.lane_perm + nl) & __ldg(sc.vtype_bit + vt))) {
+      int y = t.lane_start[nl];
+      if (t.speed[y] < kHaltSpeed && __ldg(sc.lane_len + nl) - t.pos[y] < 1.0f &&
+          (__ldg(sc.lane_perm + lane) & __ldg(sc.vtype_bit + v_vtype(t, y))) &&
+          choose_link(sc, nl, v_route(t, y), v_cursor(t, y)) == -2 &&
+          strategic_dir(sc, v_route(t, y), v_cursor(t, y), nl) == -d) {
+        target = nl;
+        vn = 0.0f;
+      }
+    }
+  }
+  vn_out = vn;
+  target_out = target >= 0 ? target : lane;
+}
+
+// ---------------------------------------------------------------------------------------------
+// block-wide exclusive prefix sum over `n` ints in shared memory (in: cnt, out: start u16[n+1])
+template <int BLOCK>
+__device__ void block_prefix(const int32_t* cnt, uint16_t* start, int n, int32_t* warp_tot) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int per = (n + BLOCK - 1) / BLOCK;
+  const int a = min(tid * per, n), b = min(a + per, n);
+  int s = 0;
+  for (int i = a; i < b; ++i) s += cnt[i];
+  int inc = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int y = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += y;
+  }
+  if (lane == 31) warp_tot[wid] = inc;
+  __syncthreads();
+  int base = 0;
+  for (int w = 0; w < wid; ++w) base += warp_tot[w];
+  int run = base + inc - s;
+  for (int i = a; i < b; ++i) { start[i] = (uint16_t)run; run += cnt[i]; }
+  if (tid == BLOCK - 1) start[n] = (uint16_t)run;
+  __syncthreads();
+}
+
+}  // namespace rs

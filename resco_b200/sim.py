@@ -1,0 +1,252 @@
+"""VecSim: Python handle on the C-ABI library (``include/resco_b200.h``).
+
+PyTorch is used only as plumbing: it owns the CUDA context/streams and wraps the borrowed device
+pointers of the observation view as tensors (zero copy).  All simulation work happens in
+``resco_b200/csrc/libresco_b200.so``; there is no CPU fallback -- constructing a VecSim without the
+library or without a Blackwell GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Dict, Optional
+
+import numpy as np
+
+from .abi import Marshalled, RsObsView, RsScenario, RsStats, STATS_DTYPE
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_CSRC, "libresco_b200.so")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC"]
+
+_LIB = None
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA extension in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(_CSRC, "sim.cu")]
+    deps = srcs + [os.path.join(_CSRC, "sim_kernels.cuh"), os.path.join(_HERE, "..", "include", "resco_b200.h")]
+    if (not force and os.path.exists(LIB_PATH)
+            and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(d) for d in deps)):
+        return LIB_PATH
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + srcs
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+EXPORTS = ["rs_last_error", "rs_abi_version", "rs_create", "rs_destroy", "rs_reset", "rs_set_phase", "rs_tick",
+           "rs_observe", "rs_env_step", "rs_env_step_host", "rs_policy_maxpressure", "rs_get_obs", "rs_get_stats",
+           "rs_dump_vehicles", "rs_get_phases", "rs_kernel_launches", "rs_last_step_ms"]
+
+
+def load_library():
+    """dlopen the in-tree library (fails loudly if it has not been built)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(the B200 backend has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    lib.rs_last_error.restype = C.c_char_p
+    lib.rs_abi_version.restype = C.c_int
+    lib.rs_create.argtypes = [C.POINTER(RsScenario), C.c_int32, C.c_int32, C.c_uint64, C.POINTER(C.c_void_p)]
+    lib.rs_destroy.argtypes = [C.c_void_p]
+    lib.rs_reset.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p]
+    lib.rs_set_phase.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.rs_tick.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    lib.rs_observe.argtypes = [C.c_void_p, C.c_void_p]
+    lib.rs_env_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.rs_env_step_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+    lib.rs_policy_maxpressure.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+                                          C.c_void_p]
+    lib.rs_get_obs.argtypes = [C.c_void_p, C.POINTER(RsObsView)]
+    lib.rs_get_stats.argtypes = [C.c_void_p, C.c_void_p]
+    lib.rs_dump_vehicles.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32)] + [C.c_void_p] * 13
+    lib.rs_get_phases.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    lib.rs_kernel_launches.restype = C.c_int64
+    lib.rs_kernel_launches.argtypes = [C.c_void_p]
+    lib.rs_last_step_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    _LIB = lib
+    return lib
+
+
+class RsError(RuntimeError):
+    pass
+
+
+def _check(lib, rc: int):
+    if rc != 0:
+        raise RsError(f"resco_b200 error {rc}: {lib.rs_last_error().decode()}")
+
+
+_VEH_FIELDS = [("lane", np.int32), ("pos", np.float32), ("speed", np.float32), ("accel", np.float32),
+               ("wait", np.float32), ("rwait", np.float32), ("tloss", np.float32), ("vid", np.int32),
+               ("vtype", np.int32), ("route", np.int32), ("cursor", np.int32), ("sf", np.float32),
+               ("depart", np.int32)]
+
+_OBS_FIELDS = [("lane_queue", "f", "L"), ("lane_approach", "f", "L"), ("lane_total_wait", "f", "L"),
+               ("lane_max_wait", "f", "L"), ("lane_speed_sum", "f", "L"), ("phase", "i", "S"),
+               ("mplight", "f", "S13"), ("wave", "f", "S12"), ("reward_wait", "f", "S"),
+               ("reward_wait_norm", "f", "S"), ("reward_pressure", "f", "S"), ("sig_queue_len", "i", "S"),
+               ("sig_max_queue", "i", "S")]
+
+
+class VecSim:
+    """N lock-step environment instances on one GPU."""
+
+    def __init__(self, m: Marshalled, n_env: int, seed: int = 0, device: int = 0):
+        import torch  # plumbing only (context, streams, tensor views)
+        self._torch = torch
+        self.lib = load_library()
+        if self.lib.rs_abi_version() != m.struct.abi_version:
+            raise RsError("ABI version mismatch between resco_b200.abi and libresco_b200.so")
+        self.m = m
+        self.n_env = n_env
+        self.S = m.struct.n_signals
+        self.SL = m.struct.n_sig_lanes
+        self.vcap = m.struct.vcap
+        self.device = device
+        h = C.c_void_p()
+        _check(self.lib, self.lib.rs_create(C.byref(m.struct), n_env, device, seed, C.byref(h)))
+        self._h = h
+        self._views: Optional[Dict[str, object]] = None
+        self._policy_tables = None
+
+    # lifecycle ---------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.rs_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(self._torch.cuda.current_stream(self.device).cuda_stream)
+
+    # simulation --------------------------------------------------------------------------------
+    def reset(self, seed: int = 0, first_env_id: int = 0):
+        _check(self.lib, self.lib.rs_reset(self._h, seed, first_env_id, self._stream()))
+
+    def set_phase(self, phase, mask=None):
+        t = self._torch
+        p = t.as_tensor(np.asarray(phase), dtype=t.int32, device=f"cuda:{self.device}").contiguous() \
+            if not t.is_tensor(phase) else phase.to(dtype=t.int32).contiguous()
+        mk = None
+        if mask is not None:
+            mk = t.as_tensor(np.asarray(mask), dtype=t.uint8, device=f"cuda:{self.device}").contiguous()
+        _check(self.lib, self.lib.rs_set_phase(self._h, p.data_ptr(), mk.data_ptr() if mk is not None else None,
+                                               self._stream()))
+
+    def tick(self, n: int = 1):
+        _check(self.lib, self.lib.rs_tick(self._h, n, self._stream()))
+
+    def observe(self):
+        _check(self.lib, self.lib.rs_observe(self._h, self._stream()))
+
+    def env_step(self, actions):
+        """actions: [N, S] int32 torch CUDA tensor (or array-like, copied H2D)."""
+        t = self._torch
+        if not t.is_tensor(actions):
+            actions = t.as_tensor(np.ascontiguousarray(actions, np.int32), device=f"cuda:{self.device}")
+        actions = actions.to(dtype=t.int32).contiguous()
+        assert actions.numel() == self.n_env * self.S
+        self._keep_actions = actions
+        _check(self.lib, self.lib.rs_env_step(self._h, actions.data_ptr(), self._stream()))
+
+    def env_step_host(self, actions: np.ndarray, reward_kind: int = 0):
+        """End-to-end call with HOST buffers (H2D actions, D2H mplight obs + reward)."""
+        a = np.ascontiguousarray(actions, np.int32)
+        obs = np.empty((self.n_env, self.S, 13), np.float32)
+        rew = np.empty((self.n_env, self.S), np.float32)
+        _check(self.lib, self.lib.rs_env_step_host(self._h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data,
+                                                   reward_kind))
+        return obs, rew
+
+    def policy_maxpressure(self, pairs, valid_acts, signal_ids, use_wave: bool = False):
+        """Batched MAXPRESSURE / MAXWAVE on the device -> [N, S] int32 CUDA tensor of actions."""
+        t = self._torch
+        if self._policy_tables is None:
+            npairs = len(pairs)
+            pr = np.ascontiguousarray(np.asarray(pairs, np.int32).reshape(-1))
+            va = np.full((self.S, npairs), -1, np.int32)
+            for i, s in enumerate(signal_ids):
+                if valid_acts is None:
+                    va[i, :] = np.arange(npairs)
+                else:
+                    for k, v in valid_acts[s].items():
+                        va[i, int(k)] = int(v)
+            self._policy_tables = (pr, np.ascontiguousarray(va), npairs)
+            self._policy_out = t.zeros((self.n_env, self.S), dtype=t.int32, device=f"cuda:{self.device}")
+        pr, va, npairs = self._policy_tables
+        _check(self.lib, self.lib.rs_policy_maxpressure(self._h, pr.ctypes.data, npairs, va.ctypes.data,
+                                                        1 if use_wave else 0, self._policy_out.data_ptr(),
+                                                        self._stream()))
+        return self._policy_out
+
+    # results -----------------------------------------------------------------------------------
+    def obs_view(self) -> Dict[str, object]:
+        """Zero-copy torch views on the device observation buffers (borrowed: valid until close())."""
+        if self._views is None:
+            t = self._torch
+            v = RsObsView()
+            _check(self.lib, self.lib.rs_get_obs(self._h, C.byref(v)))
+            shapes = {"L": (self.n_env, self.SL), "S": (self.n_env, self.S), "S13": (self.n_env, self.S, 13),
+                      "S12": (self.n_env, self.S, 12)}
+            out = {}
+            for name, kind, shp in _OBS_FIELDS:
+                ptr = getattr(v, name)
+                shape = shapes[shp]
+                n = int(np.prod(shape))
+                out[name] = _wrap_device(t, ptr, n, kind, self.device).view(*shape) if n > 0 else \
+                    t.zeros(shape, dtype=t.float32 if kind == "f" else t.int32, device=f"cuda:{self.device}")
+            self._views = out
+        return self._views
+
+    def obs(self) -> Dict[str, np.ndarray]:
+        self._torch.cuda.synchronize(self.device)
+        return {k: v.cpu().numpy() for k, v in self.obs_view().items()}
+
+    def stats(self) -> np.ndarray:
+        st = np.zeros(self.n_env, STATS_DTYPE)
+        _check(self.lib, self.lib.rs_get_stats(self._h, st.ctypes.data))
+        return st
+
+    def vehicles(self, env: int = 0) -> Dict[str, np.ndarray]:
+        arrs = {n: np.zeros(self.vcap, dt) for n, dt in _VEH_FIELDS}
+        n = C.c_int32(0)
+        _check(self.lib, self.lib.rs_dump_vehicles(self._h, env, C.byref(n),
+                                                   *[arrs[k].ctypes.data for k, _ in _VEH_FIELDS]))
+        return {k: v[:n.value] for k, v in arrs.items()}
+
+    def phases(self, env: int = 0) -> np.ndarray:
+        p = np.zeros(self.m.struct.n_tls, np.int32)
+        _check(self.lib, self.lib.rs_get_phases(self._h, env, p.ctypes.data))
+        return p
+
+    def kernel_launches(self) -> int:
+        return int(self.lib.rs_kernel_launches(self._h))
+
+    def last_step_ms(self) -> float:
+        ms = C.c_float(0)
+        _check(self.lib, self.lib.rs_last_step_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
+
+class _DevArray:
+    """Minimal __cuda_array_interface__ holder so torch can wrap a borrowed device pointer."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3,
+                                         "strides": None}
+
+
+def _wrap_device(torch, ptr: int, n: int, kind: str, device: int):
+    return torch.as_tensor(_DevArray(ptr, n, "<f4" if kind == "f" else "<i4"), device=f"cuda:{device}")
