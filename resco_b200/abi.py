@@ -258,11 +258,47 @@ def marshal(sc: Scenario, *, step_length: int = 10, yellow_length: int = 3, max_
     return Marshalled(st, keep, info)
 
 
+SMEM_BUDGET = 200 * 1024   # bytes of the 227 KB per-CTA shared memory the instance tile may use
+
+
+def smem_bytes(vcap: int, n_lanes: int, n_tls: int, n_signals: int, n_origins: int, n_sig_lanes: int,
+               n_vtypes: int) -> int:
+    """Mirror of rs::make_layout (resco_b200/csrc/sim.cu): shared memory of one instance tile."""
+    def al(x):
+        return (x + 15) & ~15
+    o = 0
+    o = al(o + 10 * vcap * 4)
+    o = al(o + 10 * vcap * 4)
+    o = al(o + vcap * 4)
+    for _ in range(4):
+        o = al(o + vcap * 2)
+    o = al(o + (n_lanes + 1) * 2)
+    o = al(o + (n_lanes + 1) * 2)
+    o = al(o + n_lanes * 4)
+    o = al(o + n_lanes * 4)
+    o = al(o + n_tls * 4)
+    o = al(o + n_tls * 4)
+    o = al(o + max(n_signals, 1) * 4)
+    o = al(o + max(n_origins, 1) * 4)
+    o = al(o + max(n_origins, 1) * 4)
+    o = al(o + max(n_origins, 1) * 16)
+    o = al(o + n_vtypes * 32)
+    o = al(o + 16 * 4)
+    o = al(o + 64 * 4)
+    o = al(o + max(n_sig_lanes, 1) * 20)
+    return o
+
+
 def default_vcap(sc: Scenario) -> int:
     """Concurrent-vehicle capacity per instance: a quarter of the jam capacity of the normal lanes,
-    rounded up to a multiple of 64 (clamped to [256, 4096])."""
+    rounded up to a multiple of 64, clamped to [256, 4096] and to what fits the shared-memory tile."""
     a = sc.arrays
     normal = a["lane_internal"] == 0
     jam = float(np.sum(np.floor(a["lane_len"][normal] / 7.5) + 1))
     v = int(np.ceil(jam / 4 / 64.0)) * 64
-    return int(min(max(v, 256), 4096))
+    v = int(min(max(v, 256), 4096))
+    n_sig_lanes = int(a["sig_lane_off"][-1]) if "sig_lane_off" in a else 0
+    while v > 64 and smem_bytes(v, sc.n_lanes, sc.n_tls, len(sc.meta["signal_ids"]), len(a["origin_lane"]),
+                                n_sig_lanes, len(a["vtype_bit"])) > SMEM_BUDGET:
+        v -= 64
+    return v
