@@ -1,0 +1,69 @@
+"""Golden vectors produced by the UNMODIFIED reference Python (tools/make_golden.py) vs our MultiSignal.
+
+CPU (`not gpu`): our MultiSignal drives the oracle's fused env-step path -> pins the oracle's RESCO-layer
+restatement (yellows, phase machine, observe latch, states, rewards, metrics, step schedule) against the
+reference itself.  GPU: the same goldens through the CUDA path (C-ABI)."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+import resco_b200.rewards as rewards
+import resco_b200.states as states
+from resco_b200.multi_signal import MultiSignal
+
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def _oracle_backend(m):
+    from pyoracle import OracleSim
+    return OracleSim(m, 1, seed=0)
+
+
+def _run_case(path, backend):
+    z = np.load(path)
+    meta = json.loads(bytes(z["meta"]).decode())
+    env = MultiSignal("golden", meta["map"], None, getattr(states, meta["state"]), getattr(rewards, meta["reward"]),
+                      step_length=meta["step_length"], yellow_length=meta["yellow_length"],
+                      max_distance=meta["max_distance"], log_dir=None, backend=backend)
+    order = meta["ts_order"]
+    assert env.ts_order == order
+    assert {ts: list(env.obs_shape[ts]) for ts in order} == meta["obs_shapes"]
+    for ts in order:          # create_yellows + installed program (traffic_signal.py:7-24,93-100)
+        assert env.signals[ts].yellow_dict == meta["yellow_dicts"][ts]
+        assert [s for _, s in env.signals[ts].phases] == [s for _, s in meta["programs"][ts]]
+        assert env.signals[ts].lanes == meta["lanes"][ts]
+        assert len(env.phases[ts]) == meta["n_actions"][ts]
+    obs = env.reset()
+    got = np.concatenate([np.asarray(obs[ts], np.float64).ravel() for ts in order])
+    np.testing.assert_allclose(got, z["reset_obs"], rtol=1e-9, atol=1e-12)
+    for step in range(z["act"].shape[0]):
+        act = {ts: int(z["act"][step, i]) for i, ts in enumerate(order)}
+        obs, rew, done, info = env.step(act)
+        got = np.concatenate([np.asarray(obs[ts], np.float64).ravel() for ts in order])
+        np.testing.assert_allclose(got, z["obs"][step], rtol=1e-6, atol=1e-9, err_msg=f"obs step {step}")
+        np.testing.assert_allclose([float(rew[ts]) for ts in order], z["rew"][step], rtol=1e-6, atol=1e-9,
+                                   err_msg=f"reward step {step}")
+        assert [env.signals[ts].phase for ts in order] == z["phase"][step].tolist(), f"phase step {step}"
+        mt = env.metrics[-1]
+        assert [mt["queue_lengths"][ts] for ts in order] == z["queue_lengths"][step].tolist()
+        assert [mt["max_queues"][ts] for ts in order] == z["max_queues"][step].tolist()
+        assert mt["step"] == z["step_time"][step]
+    env.close()
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_reference_golden_cpu(path):
+    _run_case(path, _oracle_backend)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_reference_golden_gpu(path):
+    _run_case(path, None)      # default backend = CUDA VecSim through the C-ABI
+
+
+def test_goldens_present():
+    assert len(GOLD) >= 8
