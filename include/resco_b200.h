@@ -39,7 +39,7 @@ typedef struct RsScenario {
   /* sizes */
   int32_t n_lanes, n_edges, n_links, n_foes, n_tls, n_phases, n_state_chars, n_signals;
   int32_t n_sig_lanes, n_mv_lanes, n_mvo, n_out, n_yellow;
-  int32_t n_vtypes, n_routes, n_route_steps, n_origins, n_trips, n_origin_routes;
+  int32_t n_vtypes, n_routes, n_route_steps, n_origins, n_trips, n_origin_routes, n_watch;
   /* lanes */
   const float* lane_len;
   const float* lane_vmax;
@@ -110,6 +110,10 @@ typedef struct RsScenario {
   const int32_t* origin_rate;        /* P(insert request per tick) * 2^24 */
   const int32_t* origin_route_off;   /* [n_origins+1] into origin_route */
   const int32_t* origin_route;
+  /* insertion safety: lanes within 60 m upstream of each origin lane */
+  const int32_t* origin_watch_off;   /* [n_origins+1] */
+  const int32_t* origin_watch_lane;
+  const float* origin_watch_dist;    /* end of watch lane -> start of origin lane (m) */
   /* parameters */
   int32_t synthetic;
   int32_t synthetic_vtype;

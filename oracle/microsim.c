@@ -579,6 +579,24 @@ static void tick_instance(OrcSim* s, Inst* in) {
         const Veh* tl = &in->veh2[b - 1];
         if (tl->pos - VT(s, tl->vtype, VT_LEN) - len - mingap < 0.0f) ok = 0;
       }
+      /* upstream safety: nobody who is about to drive onto this lane may be forced into hard braking */
+      for (int w = sc->origin_watch_off[o]; ok && w < sc->origin_watch_off[o + 1]; ++w) {
+        int pl = sc->origin_watch_lane[w];
+        if (in->lane_start2[pl + 1] <= in->lane_start2[pl]) continue;
+        const Veh* h = &in->veh2[in->lane_start2[pl]];
+        int cur = pl, cc = h->cursor, reaches = 0;
+        for (int hop = 0; hop < 4; ++hop) {
+          int k = choose_link(sc, cur, h->route, cc);
+          if (k < 0) break;
+          int nxt = sc->link_via[k] >= 0 ? sc->link_via[k] : sc->link_to[k];
+          if (nxt == lane) { reaches = 1; break; }
+          if (!sc->lane_internal[nxt]) cc += 1;
+          cur = nxt;
+        }
+        if (!reaches) continue;
+        float gap = (sc->lane_len[pl] - h->pos) + sc->origin_watch_dist[w] - VT(s, h->vtype, VT_GAP);
+        if (gap < brake_gap(h->speed, VT(s, h->vtype, VT_DECEL), VT(s, h->vtype, VT_TAU))) ok = 0;
+      }
       if (ok) {
         Veh nv; memset(&nv, 0, sizeof nv);
         nv.pos = len; nv.speed = 0.0f; nv.vid = vid; nv.vtype = vt; nv.route = route; nv.cursor = 0;
@@ -736,6 +754,7 @@ OrcSim* orc_create(const RsScenario* sc, int32_t n_env, uint64_t seed) {
   DUP(trip_file, sc->n_trips, int32_t);
   DUP(origin_rate, sc->n_origins, int32_t); DUP(origin_route_off, sc->n_origins + 1, int32_t);
   DUP(origin_route, sc->n_origin_routes, int32_t);
+  DUP(origin_watch_off, sc->n_origins + 1, int32_t); DUP(origin_watch_lane, sc->n_watch, int32_t); DUP(origin_watch_dist, sc->n_watch, float);
   s->inst = (Inst*)calloc((size_t)n_env, sizeof(Inst));
   int V = sc->vcap, SL = sc->n_sig_lanes;
   for (int e = 0; e < n_env; ++e) {

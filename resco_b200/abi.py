@@ -20,7 +20,7 @@ _U8P = C.POINTER(C.c_uint8)
 
 _SIZES = ["n_lanes", "n_edges", "n_links", "n_foes", "n_tls", "n_phases", "n_state_chars", "n_signals",
           "n_sig_lanes", "n_mv_lanes", "n_mvo", "n_out", "n_yellow",
-          "n_vtypes", "n_routes", "n_route_steps", "n_origins", "n_trips", "n_origin_routes"]
+          "n_vtypes", "n_routes", "n_route_steps", "n_origins", "n_trips", "n_origin_routes", "n_watch"]
 
 _PTRS: List[Tuple[str, object]] = [
     ("lane_len", _F32P), ("lane_vmax", _F32P), ("lane_edge", _I32P), ("lane_index", _I32P),
@@ -41,6 +41,7 @@ _PTRS: List[Tuple[str, object]] = [
     ("route_mask", _I32P), ("origin_lane", _I32P), ("origin_off", _I32P), ("trip_depart", _F32P),
     ("trip_route", _I32P), ("trip_vtype", _I32P), ("trip_file", _I32P),
     ("origin_rate", _I32P), ("origin_route_off", _I32P), ("origin_route", _I32P),
+    ("origin_watch_off", _I32P), ("origin_watch_lane", _I32P), ("origin_watch_dist", _F32P),
 ]
 
 _PARAMS = [("synthetic", C.c_int32), ("synthetic_vtype", C.c_int32), ("step_length", C.c_int32),
@@ -209,7 +210,8 @@ def marshal(sc: Scenario, *, step_length: int = 10, yellow_length: int = 3, max_
         n_mv_lanes=len(a["mv_lane"]) if controlled else 0, n_mvo=len(a["mvo_sig"]) if controlled else 0,
         n_out=len(a["out_sig"]) if controlled else 0, n_yellow=len(yellow_idx),
         n_vtypes=len(a["vtype_bit"]), n_routes=len(a["route_off"]) - 1, n_route_steps=len(a["route_edge"]),
-        n_origins=len(a["origin_lane"]), n_trips=n_trips, n_origin_routes=0)
+        n_origins=len(a["origin_lane"]), n_trips=n_trips, n_origin_routes=0,
+        n_watch=len(a["origin_watch_lane"]))
     arrays: Dict[str, Tuple[object, object]] = {}
     for name, ct in _PTRS:
         if name in a:
@@ -228,8 +230,11 @@ def marshal(sc: Scenario, *, step_length: int = 10, yellow_length: int = 3, max_
         for nm in ("sig_lane_off", "mv_off", "mvo_off", "out_off"):
             arrays[nm] = (np.zeros(1, np.int32), np.int32)
     if synthetic is not None:
-        for nm in ("origin_lane", "origin_rate", "origin_route_off", "origin_route"):
+        for nm in ("origin_lane", "origin_rate", "origin_route_off", "origin_route", "origin_watch_off",
+                   "origin_watch_lane"):
             arrays[nm] = (synthetic[nm], np.int32)
+        arrays["origin_watch_dist"] = (synthetic["origin_watch_dist"], np.float32)
+        sizes["n_watch"] = len(synthetic["origin_watch_lane"])
         sizes["n_origins"] = len(synthetic["origin_lane"])
         sizes["n_origin_routes"] = len(synthetic["origin_route"])
         sizes["n_trips"] = 0

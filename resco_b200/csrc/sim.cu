@@ -218,6 +218,35 @@ __device__ void tick_body(const DevSim& D, const SmemLayout& m, unsigned char* s
           if (T.pos[tailv] - VTT(T, tvt, VT_LEN) - len - mingap < 0.0f) ok = false;
         }
       }
+      // upstream safety: nobody about to drive onto this lane may be forced into hard braking
+      for (int w = __ldg(sc.origin_watch_off + o); ok && w < __ldg(sc.origin_watch_off + o + 1); ++w) {
+        int pl = __ldg(sc.origin_watch_lane + w);
+        // post-move head of pl: first stayer of the old segment vs. the front-most mover into pl
+        int a = T.lane_start[pl], b = T.lane_start[pl + 1];
+        int hs = -1;
+        for (int i = a; i < b; ++i) if (newlane[i] == pl) { hs = i; break; }
+        int hm = -1;
+        for (int q = mhead[pl]; q >= 0; q = (mnext[q] == 0xFFFF ? -1 : (int)mnext[q]))
+          if (hm < 0 || T.pos[q] > T.pos[hm] || (T.pos[q] == T.pos[hm] && q < hm)) hm = q;
+        int h = hs;
+        if (hm >= 0 && (hs < 0 || T.pos[hm] > T.pos[hs])) h = hm;
+        if (h < 0) continue;
+        int cur = pl, cc = v_cursor(T, h), hr = v_route(T, h);
+        bool reaches = false;
+        for (int hop = 0; hop < 4; ++hop) {
+          int k = choose_link(sc, cur, hr, cc);
+          if (k < 0) break;
+          int via = __ldg(sc.link_via + k);
+          int nxt = via >= 0 ? via : __ldg(sc.link_to + k);
+          if (nxt == lane) { reaches = true; break; }
+          if (!__ldg(sc.lane_internal + nxt)) cc += 1;
+          cur = nxt;
+        }
+        if (!reaches) continue;
+        int hvt = v_vtype(T, h);
+        float gap = (__ldg(sc.lane_len + pl) - T.pos[h]) + __ldg(sc.origin_watch_dist + w) - VTT(T, hvt, VT_GAP);
+        if (gap < brake_gap(T.speed[h], VTT(T, hvt, VT_DECEL), VTT(T, hvt, VT_TAU))) ok = false;
+      }
       if (ok) { c.ok_dd = dd; atomicAdd(&misc[M_NOK], 1); }
     }
     cand[o] = c;
@@ -740,6 +769,8 @@ extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, ui
   TRY(dev_dup(s, d.trip_vtype, sc->n_trips)); TRY(dev_dup(s, d.trip_file, sc->n_trips));
   TRY(dev_dup(s, d.origin_rate, sc->n_origins)); TRY(dev_dup(s, d.origin_route_off, sc->n_origins + 1));
   TRY(dev_dup(s, d.origin_route, sc->n_origin_routes));
+  TRY(dev_dup(s, d.origin_watch_off, sc->n_origins + 1)); TRY(dev_dup(s, d.origin_watch_lane, sc->n_watch));
+  TRY(dev_dup(s, d.origin_watch_dist, sc->n_watch));
   const size_t N = (size_t)n_env;
   TRY(dev_alloc(s, s->d.hdr, N * kHdrInts));
   TRY(dev_alloc(s, s->d.tls_phase, N * sc->n_tls)); TRY(dev_alloc(s, s->d.tls_end, N * sc->n_tls));

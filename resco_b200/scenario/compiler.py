@@ -599,6 +599,43 @@ def compile_tls_dist(arrays: Dict[str, np.ndarray]) -> np.ndarray:
     return out
 
 
+def compile_watch(arrays: Dict[str, np.ndarray], origin_lanes: Sequence[int], reach: float = 60.0
+                  ) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Per origin lane: the lanes within `reach` metres upstream (reverse BFS over links) and the
+    distance from the END of each to the START of the origin lane.  Used by the insertion safety
+    check against vehicles that are about to drive onto the origin lane."""
+    a = arrays
+    L = len(a["lane_len"])
+    preds: List[List[int]] = [[] for _ in range(L)]
+    for k in range(len(a["link_from"])):
+        nxt = int(a["link_via"][k]) if a["link_via"][k] >= 0 else int(a["link_to"][k])
+        fl = int(a["link_from"][k])
+        if fl not in preds[nxt]:
+            preds[nxt].append(fl)
+    off = [0]
+    lanes: List[int] = []
+    dists: List[float] = []
+    for o in origin_lanes:
+        seen = {}
+        frontier = [(int(o), 0.0)]
+        while frontier:
+            nxt_frontier = []
+            for lane, d in frontier:
+                for p in sorted(preds[lane]):
+                    if p in seen and seen[p] <= d:
+                        continue
+                    seen[p] = d
+                    dp = d + float(a["lane_len"][p])
+                    if dp < reach:
+                        nxt_frontier.append((p, dp))
+            frontier = nxt_frontier
+        for p in sorted(seen):
+            lanes.append(p)
+            dists.append(seen[p])
+        off.append(len(lanes))
+    return (np.array(off, np.int32), np.array(lanes, np.int32).reshape(-1), np.array(dists, np.float32).reshape(-1))
+
+
 def compile_scenario(net: Net, demand: Optional[Demand], map_name: str, map_config: Dict[str, object],
                      signal_config: Dict[str, object], begin: float) -> Scenario:
     arrays, meta, idx = compile_net(net)
@@ -610,6 +647,9 @@ def compile_scenario(net: Net, demand: Optional[Demand], map_name: str, map_conf
     arrays.update(sarr)
     meta.update(smeta)
     arrays["lane_tls_dist"] = compile_tls_dist(arrays)
+    if "origin_lane" in arrays:
+        w_off, w_lane, w_dist = compile_watch(arrays, arrays["origin_lane"].tolist())
+        arrays.update(origin_watch_off=w_off, origin_watch_lane=w_lane, origin_watch_dist=w_dist)
     meta.update(dict(map_name=map_name, begin=begin,
                      map_config={k: v for k, v in map_config.items() if k not in ('net', 'route')},
                      phase_pairs=signal_config.get('phase_pairs'),
