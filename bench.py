@@ -36,7 +36,7 @@ sys.path.insert(0, ROOT)
 
 MAP = "cologne8"
 N_ENV_PER_GPU = 4096
-VCAP = 256
+VCAP = 128   # cologne8/MaxPressure peaks at ~110 concurrent vehicles per instance (32-seed CPU check); a full tile only delays insertions
 
 
 def _marshal(map_name=MAP, vcap=VCAP):
@@ -290,7 +290,7 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.map} (8 signals) / MaxPressure / {n_env} lock-step instances per GPU",
                        "n_env_per_gpu": n_env, "n_env_total": total_env, "sim_ticks_per_env_step": m.struct.step_length,
-                       "vcap": m.struct.vcap, "block_threads": int(os.environ.get("RESCO_B200_BLOCK", "128")),
+                       "vcap": m.struct.vcap, "block_threads": int(os.environ.get("RESCO_B200_BLOCK", "128")), "regs_per_thread": 64 if os.environ.get("RESCO_B200_REGCAP", "1") != "0" else "uncapped", "persistent_grid": os.environ.get("RESCO_B200_PERSIST", "1") != "0",
                        "l2": "flushed between timed steps (256 MiB memset, untimed)",
                        "timing": "per-step CUDA events on the launching stream, summed; max over ranks",
                        "allgather_obs": bool(gather_buf is not None),

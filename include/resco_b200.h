@@ -114,6 +114,7 @@ typedef struct RsScenario {
   const int32_t* origin_watch_off;   /* [n_origins+1] */
   const int32_t* origin_watch_lane;
   const float* origin_watch_dist;    /* end of watch lane -> start of origin lane (m) */
+  const int32_t* origin_watch_owner; /* [n_watch] origin index of each entry */
   /* parameters */
   int32_t synthetic;
   int32_t synthetic_vtype;
@@ -186,8 +187,10 @@ int rs_env_step(RsSim* sim, const int32_t* d_actions, void* stream);
  * obs/reward back; h_obs [N,S,13] mplight, h_reward [N,S] (kind: 0 wait, 1 wait_norm, 2 pressure). */
 int rs_env_step_host(RsSim* sim, const int32_t* h_actions, float* h_obs, float* h_reward, int32_t reward_kind);
 /* Batched MaxPressure / MaxWave action selection on the device (agents/maxwave.py:18-38 over
- * states.mplight[1:] / states.wave): writes [N,S] actions.  pairs [n_pairs,2]; valid [S, n_pairs] -> action or -1 */
-int rs_policy_maxpressure(RsSim* sim, const int32_t* h_pairs, int32_t n_pairs, const int32_t* h_valid,
+ * states.mplight[1:] / states.wave): writes [N,S] actions.  pairs [n_pairs,2]; order [S, n_pairs, 2] =
+ * (pair index, action) in the reference's evaluation order (iteration order of valid_acts[signal]),
+ * pair index -1 terminates a row; ties resolve to the first maximum like the reference's strict '>'. */
+int rs_policy_maxpressure(RsSim* sim, const int32_t* h_pairs, int32_t n_pairs, const int32_t* h_order,
                           int32_t use_wave, int32_t* d_actions_out, void* stream);
 int rs_get_obs(RsSim* sim, RsObsView* out);
 int rs_get_stats(RsSim* sim, RsStats* h_out /* [N] */);

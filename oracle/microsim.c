@@ -754,7 +754,7 @@ OrcSim* orc_create(const RsScenario* sc, int32_t n_env, uint64_t seed) {
   DUP(trip_file, sc->n_trips, int32_t);
   DUP(origin_rate, sc->n_origins, int32_t); DUP(origin_route_off, sc->n_origins + 1, int32_t);
   DUP(origin_route, sc->n_origin_routes, int32_t);
-  DUP(origin_watch_off, sc->n_origins + 1, int32_t); DUP(origin_watch_lane, sc->n_watch, int32_t); DUP(origin_watch_dist, sc->n_watch, float);
+  DUP(origin_watch_off, sc->n_origins + 1, int32_t); DUP(origin_watch_lane, sc->n_watch, int32_t); DUP(origin_watch_dist, sc->n_watch, float); DUP(origin_watch_owner, sc->n_watch, int32_t);
   s->inst = (Inst*)calloc((size_t)n_env, sizeof(Inst));
   int V = sc->vcap, SL = sc->n_sig_lanes;
   for (int e = 0; e < n_env; ++e) {

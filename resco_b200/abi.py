@@ -42,6 +42,7 @@ _PTRS: List[Tuple[str, object]] = [
     ("trip_route", _I32P), ("trip_vtype", _I32P), ("trip_file", _I32P),
     ("origin_rate", _I32P), ("origin_route_off", _I32P), ("origin_route", _I32P),
     ("origin_watch_off", _I32P), ("origin_watch_lane", _I32P), ("origin_watch_dist", _F32P),
+    ("origin_watch_owner", _I32P),
 ]
 
 _PARAMS = [("synthetic", C.c_int32), ("synthetic_vtype", C.c_int32), ("step_length", C.c_int32),
@@ -224,6 +225,7 @@ def marshal(sc: Scenario, *, step_length: int = 10, yellow_length: int = 3, max_
         state_chars=(np.frombuffer(bytes(chars), np.uint8), np.uint8),
         sig_tls=(sig_tls, np.int32), sig_n_green=(sig_n_green, np.int32),
         sig_yellow_off=(sig_yellow_off, np.int32), yellow_idx=(yellow_idx, np.int32),
+        origin_watch_owner=(np.repeat(np.arange(len(a["origin_lane"])), np.diff(a["origin_watch_off"])), np.int32),
         origin_rate=(np.zeros(1, np.int32), np.int32), origin_route_off=(np.zeros(sizes["n_origins"] + 1, np.int32), np.int32),
         origin_route=(np.zeros(1, np.int32), np.int32))
     if not controlled:
@@ -235,6 +237,8 @@ def marshal(sc: Scenario, *, step_length: int = 10, yellow_length: int = 3, max_
             arrays[nm] = (synthetic[nm], np.int32)
         arrays["origin_watch_dist"] = (synthetic["origin_watch_dist"], np.float32)
         sizes["n_watch"] = len(synthetic["origin_watch_lane"])
+        arrays["origin_watch_owner"] = (np.repeat(np.arange(len(synthetic["origin_lane"])),
+                                                  np.diff(synthetic["origin_watch_off"])), np.int32)
         sizes["n_origins"] = len(synthetic["origin_lane"])
         sizes["n_origin_routes"] = len(synthetic["origin_route"])
         sizes["n_trips"] = 0
@@ -286,7 +290,7 @@ def smem_bytes(vcap: int, n_lanes: int, n_tls: int, n_signals: int, n_origins: i
     o = al(o + max(n_signals, 1) * 4)
     o = al(o + max(n_origins, 1) * 4)
     o = al(o + max(n_origins, 1) * 4)
-    o = al(o + max(n_origins, 1) * 16)
+    o = al(o + max(n_origins, 1) * 20)
     o = al(o + n_vtypes * 32)
     o = al(o + 16 * 4)
     o = al(o + 64 * 4)

@@ -47,7 +47,7 @@ __host__ __device__ inline SmemLayout make_layout(const RsScenario& sc) {
   m.off_next_phase = o; o = align16(o + (size_t)(m.S > 0 ? m.S : 1) * 4);
   m.off_origin_cur = o; o = align16(o + (size_t)(m.O > 0 ? m.O : 1) * 4);
   m.off_origin_backlog = o; o = align16(o + (size_t)(m.O > 0 ? m.O : 1) * 4);
-  m.off_origin_cand = o; o = align16(o + (size_t)(m.O > 0 ? m.O : 1) * 16);
+  m.off_origin_cand = o; o = align16(o + (size_t)(m.O > 0 ? m.O : 1) * 20);
   m.off_vt = o; o = align16(o + (size_t)m.n_vt * 8 * 4);
   m.off_hdr = o; o = align16(o + (size_t)kHdrInts * 4);
   m.off_misc = o; o = align16(o + 64 * 4);
@@ -59,7 +59,7 @@ __host__ __device__ inline SmemLayout make_layout(const RsScenario& sc) {
 // misc slots
 enum { M_NARR = 0, M_NOK, M_NAFTER, M_WARP = 16 /* 32 ints of warp totals */ };
 
-struct OriginCand { int32_t route, vt, vid, ok_dd; };   // ok_dd: -1 not ok, else depart delay
+struct OriginCand { int32_t route, vt, vid, ok_dd, unsafe; };   // ok_dd: -1 not ok, else depart delay
 
 // ------------------------------------------------------------------------------------------------
 template <int BLOCK>
@@ -127,7 +127,7 @@ __device__ void tick_body(const DevSim& D, const SmemLayout& m, unsigned char* s
     else {
       int guard = 0;
       while (p > __ldg(sc.lane_len + curl) && guard++ < 64) {
-        int k = choose_link(sc, curl, route, cc);
+        int k = guard == 1 ? v_nextlink(sc, T, i, l) : choose_link(sc, curl, route, cc);
         if (k == -1) { curl = -1; break; }
         if (k == -2) { p = __ldg(sc.lane_len + curl); break; }
         p -= __ldg(sc.lane_len + curl);
@@ -138,7 +138,9 @@ __device__ void tick_body(const DevSim& D, const SmemLayout& m, unsigned char* s
     }
     T.pos[i] = p;
     T.rc[i] = (T.rc[i] & 0xFFFFu) | ((uint32_t)cc << 16);
-    T.meta[i] = (T.meta[i] & 0xFFFF00FFu) | ((uint32_t)lcc << 8);
+    uint32_t mt = (T.meta[i] & 0xFFFF00FFu) | ((uint32_t)lcc << 8);
+    if (curl >= 0 && curl != l) mt = (mt & 0x00FFFFFFu) | (encode_nextlink(sc, curl, choose_link(sc, curl, route, cc)) << 24);
+    T.meta[i] = mt;
     if (curl < 0) {
       newlane[i] = (uint16_t)kArrived;
       atomicAdd(&cnt2[l], -1);
@@ -174,7 +176,7 @@ __device__ void tick_body(const DevSim& D, const SmemLayout& m, unsigned char* s
   }
   for (int o = tid; o < m.O; o += BLOCK) {
     int lane = __ldg(sc.origin_lane + o);
-    OriginCand c; c.ok_dd = -1; c.route = 0; c.vt = 0; c.vid = 0;
+    OriginCand c; c.ok_dd = -1; c.route = 0; c.vt = 0; c.vid = 0; c.unsafe = 0;
     bool have = false;
     int dd = 0;
     if (sc.synthetic) {
@@ -218,38 +220,48 @@ __device__ void tick_body(const DevSim& D, const SmemLayout& m, unsigned char* s
           if (T.pos[tailv] - VTT(T, tvt, VT_LEN) - len - mingap < 0.0f) ok = false;
         }
       }
-      // upstream safety: nobody about to drive onto this lane may be forced into hard braking
-      for (int w = __ldg(sc.origin_watch_off + o); ok && w < __ldg(sc.origin_watch_off + o + 1); ++w) {
-        int pl = __ldg(sc.origin_watch_lane + w);
-        // post-move head of pl: first stayer of the old segment vs. the front-most mover into pl
-        int a = T.lane_start[pl], b = T.lane_start[pl + 1];
-        int hs = -1;
-        for (int i = a; i < b; ++i) if (newlane[i] == pl) { hs = i; break; }
-        int hm = -1;
-        for (int q = mhead[pl]; q >= 0; q = (mnext[q] == 0xFFFF ? -1 : (int)mnext[q]))
-          if (hm < 0 || T.pos[q] > T.pos[hm] || (T.pos[q] == T.pos[hm] && q < hm)) hm = q;
-        int h = hs;
-        if (hm >= 0 && (hs < 0 || T.pos[hm] > T.pos[hs])) h = hm;
-        if (h < 0) continue;
-        int cur = pl, cc = v_cursor(T, h), hr = v_route(T, h);
-        bool reaches = false;
-        for (int hop = 0; hop < 4; ++hop) {
-          int k = choose_link(sc, cur, hr, cc);
-          if (k < 0) break;
-          int via = __ldg(sc.link_via + k);
-          int nxt = via >= 0 ? via : __ldg(sc.link_to + k);
-          if (nxt == lane) { reaches = true; break; }
-          if (!__ldg(sc.lane_internal + nxt)) cc += 1;
-          cur = nxt;
-        }
-        if (!reaches) continue;
-        int hvt = v_vtype(T, h);
-        float gap = (__ldg(sc.lane_len + pl) - T.pos[h]) + __ldg(sc.origin_watch_dist + w) - VTT(T, hvt, VT_GAP);
-        if (gap < brake_gap(T.speed[h], VTT(T, hvt, VT_DECEL), VTT(T, hvt, VT_TAU))) ok = false;
-      }
-      if (ok) { c.ok_dd = dd; atomicAdd(&misc[M_NOK], 1); }
+      if (ok) c.ok_dd = dd;
     }
     cand[o] = c;
+  }
+  __syncthreads();
+
+  // ---- S3a': upstream safety of the candidates, one thread per (origin, watch lane) pair:
+  //      nobody who is about to drive onto an origin lane may be forced into hard braking ----
+  for (int w = tid; w < sc.n_watch; w += BLOCK) {
+    int o = __ldg(sc.origin_watch_owner + w);
+    if (cand[o].ok_dd < 0) continue;
+    int lane = __ldg(sc.origin_lane + o);
+    int pl = __ldg(sc.origin_watch_lane + w);
+    // post-move head of pl: first stayer of the old segment vs. the front-most mover into pl
+    int a = T.lane_start[pl], b = T.lane_start[pl + 1];
+    int hs = -1;
+    for (int i = a; i < b; ++i) if (newlane[i] == pl) { hs = i; break; }
+    int hm = -1;
+    for (int q = mhead[pl]; q >= 0; q = (mnext[q] == 0xFFFF ? -1 : (int)mnext[q]))
+      if (hm < 0 || T.pos[q] > T.pos[hm] || (T.pos[q] == T.pos[hm] && q < hm)) hm = q;
+    int h = hs;
+    if (hm >= 0 && (hs < 0 || T.pos[hm] > T.pos[hs])) h = hm;
+    if (h < 0) continue;
+    int cur = pl, cc = v_cursor(T, h), hr = v_route(T, h);
+    bool reaches = false;
+    for (int hop = 0; hop < 4; ++hop) {
+      int k = hop == 0 ? v_nextlink(sc, T, h, pl) : choose_link(sc, cur, hr, cc);
+      if (k < 0) break;
+      int via = __ldg(sc.link_via + k);
+      int nxt = via >= 0 ? via : __ldg(sc.link_to + k);
+      if (nxt == lane) { reaches = true; break; }
+      if (!__ldg(sc.lane_internal + nxt)) cc += 1;
+      cur = nxt;
+    }
+    if (!reaches) continue;
+    int hvt = v_vtype(T, h);
+    float gap = (__ldg(sc.lane_len + pl) - T.pos[h]) + __ldg(sc.origin_watch_dist + w) - VTT(T, hvt, VT_GAP);
+    if (gap < brake_gap(T.speed[h], VTT(T, hvt, VT_DECEL), VTT(T, hvt, VT_TAU))) cand[o].unsafe = 1;
+  }
+  __syncthreads();
+  for (int o = tid; o < m.O; o += BLOCK) {
+    if (cand[o].ok_dd >= 0) { if (cand[o].unsafe) cand[o].ok_dd = -1; else atomicAdd(&misc[M_NOK], 1); }
   }
   __syncthreads();
 
@@ -326,7 +338,7 @@ __device__ void tick_body(const DevSim& D, const SmemLayout& m, unsigned char* s
       float dev = sc.speed_dev_override >= 0.0f ? sc.speed_dev_override : VTT(T, c.vt, VT_DEV);
       U.pos[d] = VTT(T, c.vt, VT_LEN); U.speed[d] = 0.0f; U.sf[d] = speed_factor(T, c.vid, dev); U.tloss[d] = 0.0f;
       U.vid[d] = c.vid; U.wr[d] = 0u; U.rc[d] = (uint32_t)c.route;
-      U.meta[d] = (uint32_t)c.vt | (0xFFu << 16);
+      U.meta[d] = (uint32_t)c.vt | (0xFFu << 16) | (encode_nextlink(sc, lane, choose_link(sc, lane, c.route, 0)) << 24);
       U.ed[d] = 0xFFFEu | ((uint32_t)T.tick << 16);
       U.dl[d] = (uint32_t)(c.ok_dd & 0xFFFF) | ((uint32_t)lane << 16);
     }
@@ -453,11 +465,10 @@ __device__ __forceinline__ void dev_set_phase(const RsScenario& sc, Tile& T, int
 }
 
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_run(DevSim D, RunArgs A) {
-  extern __shared__ __align__(16) unsigned char smem[];
+__device__ __forceinline__ void run_instance(const DevSim& D, const RunArgs& A, const SmemLayout& m,
+                                             unsigned char* smem, const int env) {
   const RsScenario& sc = D.sc;
-  const SmemLayout m = make_layout(sc);
-  const int env = blockIdx.x, tid = threadIdx.x;
+  const int tid = threadIdx.x;
   uint32_t* cur = (uint32_t*)(smem + m.off_bufA);
   uint32_t* oth = (uint32_t*)(smem + m.off_bufB);
   int32_t* hdr = (int32_t*)(smem + m.off_hdr);
@@ -525,12 +536,16 @@ __global__ void __launch_bounds__(BLOCK) k_run(DevSim D, RunArgs A) {
     }
     __syncthreads();
   }
-  for (int k = 0; k < A.ticks_a; ++k) tick_body<BLOCK>(D, m, smem, T, cur, oth);
-  if (A.do_set) {
-    for (int sg = tid; sg < m.S; sg += BLOCK) dev_set_phase(sc, T, sg, next_phase[sg]);
-    __syncthreads();
+  const int n_ticks = A.ticks_a + A.ticks_b;
+#pragma unroll 1
+  for (int k = 0; k <= n_ticks; ++k) {
+    if (k == A.ticks_a && A.do_set) {   // Signal.set_phase after the yellow interval
+      for (int sg = tid; sg < m.S; sg += BLOCK) dev_set_phase(sc, T, sg, next_phase[sg]);
+      __syncthreads();
+    }
+    if (k == n_ticks) break;
+    tick_body<BLOCK>(D, m, smem, T, cur, oth);
   }
-  for (int k = 0; k < A.ticks_b; ++k) tick_body<BLOCK>(D, m, smem, T, cur, oth);
   if (A.do_observe) observe_body<BLOCK>(D, m, smem, T, env);
 
   // ---- write the tile back ----
@@ -553,6 +568,25 @@ __global__ void __launch_bounds__(BLOCK) k_run(DevSim D, RunArgs A) {
   for (int i = tid; i < m.O; i += BLOCK) {
     D.origin_cur[(size_t)env * m.O + i] = origin_cur[i];
     D.origin_backlog[(size_t)env * m.O + i] = origin_backlog[i];
+  }
+}
+
+// Persistent launch: the grid holds as many CTAs as are resident at once (148 SMs x CTAs/SM); each
+// CTA pulls the next environment instance from a global counter until all N are stepped, so there
+// is no partial last wave and uneven instances balance out.
+template <int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_run(DevSim D, RunArgs A) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const SmemLayout m = make_layout(D.sc);
+  if (!D.persistent) { run_instance<BLOCK>(D, A, m, smem, blockIdx.x); return; }
+  __shared__ int s_env;
+  for (;;) {
+    if (threadIdx.x == 0) s_env = atomicAdd(D.work_counter, 1);
+    __syncthreads();
+    const int env = s_env;
+    if (env >= D.n_env) break;
+    run_instance<BLOCK>(D, A, m, smem, env);
+    __syncthreads();
   }
 }
 
@@ -619,9 +653,11 @@ __global__ void k_stats(DevSim D, RsStats* out) {
   out[env] = st;
 }
 
-// Batched WaveAgent.act (agents/maxwave.py:18-38): argmax over valid phase pairs of obs[p0]+obs[p1].
+// Batched WaveAgent.act (agents/maxwave.py:18-38): first maximum, in the reference's evaluation order
+// (the iteration order of valid_acts[signal]), of obs[p0] + obs[p1] over the valid phase pairs.
 // obs = states.mplight[1:] (MAXPRESSURE, agents/maxpressure.py:13-18) or states.wave (MAXWAVE).
-__global__ void k_policy(DevSim D, const int32_t* pairs, int n_pairs, const int32_t* valid, int use_wave,
+// order: [S][n_pairs][2] = (pair index, action) in evaluation order, pair index -1 terminates.
+__global__ void k_policy(DevSim D, const int32_t* pairs, int n_pairs, const int32_t* order, int use_wave,
                          int32_t* actions) {
   const RsScenario& sc = D.sc;
   int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -629,11 +665,11 @@ __global__ void k_policy(DevSim D, const int32_t* pairs, int n_pairs, const int3
   int sg = x % sc.n_signals;
   const float* ob = use_wave ? D.wave + (size_t)x * 12 : D.mplight + (size_t)x * 13 + 1;
   float best = 0.0f; int bi = -1;
-  for (int p = 0; p < n_pairs; ++p) {
-    int act = valid[sg * n_pairs + p];
-    if (act < 0) continue;
+  for (int k = 0; k < n_pairs; ++k) {
+    int p = order[(sg * n_pairs + k) * 2];
+    if (p < 0) break;
     float pr = ob[pairs[2 * p]] + ob[pairs[2 * p + 1]];
-    if (bi < 0 || pr > best) { best = pr; bi = act; }
+    if (bi < 0 || pr > best) { best = pr; bi = order[(sg * n_pairs + k) * 2 + 1]; }
   }
   actions[x] = bi < 0 ? 0 : bi;
 }
@@ -650,6 +686,10 @@ struct RsSim {
   SmemLayout layout;
   int device;
   int block;
+  int minb;
+  int carveout;
+  int n_sm;
+  int resident_ctas;
   std::vector<void*> allocs;
   int64_t launches;
   cudaEvent_t ev0, ev1;
@@ -692,34 +732,41 @@ static int dev_alloc(RsSim* s, T*& out, size_t count) {
 }
 #define TRY(x) do { int _r = (x); if (_r) return _r; } while (0)
 
-template <int BLOCK>
+template <int BLOCK, int MINB>
 static int launch_run(RsSim* s, const RunArgs& a, cudaStream_t st) {
-  k_run<BLOCK><<<s->d.n_env, BLOCK, s->layout.total, st>>>(s->d, a);
+  int grid = s->d.n_env;
+  if (s->d.persistent) {
+    CK(cudaMemsetAsync(s->d.work_counter, 0, sizeof(int32_t), st));
+    if (s->resident_ctas < grid) grid = s->resident_ctas;
+  }
+  k_run<BLOCK, MINB><<<grid, BLOCK, s->layout.total, st>>>(s->d, a);
   s->launches += 1;
   CK(cudaGetLastError());
   return 0;
 }
 
+// variant = block threads * 10 + (1 if registers are capped at 64/thread for occupancy)
+#define RS_VARIANTS(X) X(32, 1) X(32, 32) X(64, 1) X(64, 16) X(128, 1) X(128, 8) X(256, 1) X(256, 4)
+
 static int run(RsSim* s, const RunArgs& a, cudaStream_t st) {
-  switch (s->block) {
-    case 32: return launch_run<32>(s, a, st);
-    case 64: return launch_run<64>(s, a, st);
-    case 128: return launch_run<128>(s, a, st);
-    case 256: return launch_run<256>(s, a, st);
-    default: return fail(RS_ERR_INVALID, "block size must be 32/64/128/256");
-  }
+#define X(B, M) if (s->block == B && s->minb == M) return launch_run<B, M>(s, a, st);
+  RS_VARIANTS(X)
+#undef X
+  return fail(RS_ERR_INVALID, "unsupported RESCO_B200_BLOCK / RESCO_B200_REGCAP combination");
 }
 
 static int configure(RsSim* s) {
   const int bytes = (int)s->layout.total;
-  switch (s->block) {
-    case 32: CK(cudaFuncSetAttribute(k_run<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); break;
-    case 64: CK(cudaFuncSetAttribute(k_run<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); break;
-    case 128: CK(cudaFuncSetAttribute(k_run<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); break;
-    case 256: CK(cudaFuncSetAttribute(k_run<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); break;
-    default: return fail(RS_ERR_INVALID, "RESCO_B200_BLOCK must be 32/64/128/256");
-  }
-  return 0;
+#define X(B, M) if (s->block == B && s->minb == M) { \
+    CK(cudaFuncSetAttribute(k_run<B, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); \
+    if (s->carveout >= 0) CK(cudaFuncSetAttribute(k_run<B, M>, cudaFuncAttributePreferredSharedMemoryCarveout, s->carveout)); \
+    int per_sm = 0; \
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_run<B, M>, B, bytes)); \
+    s->resident_ctas = (per_sm > 0 ? per_sm : 1) * s->n_sm; \
+    return 0; }
+  RS_VARIANTS(X)
+#undef X
+  return fail(RS_ERR_INVALID, "RESCO_B200_BLOCK must be 32/64/128/256 (RESCO_B200_REGCAP 0/1)");
 }
 
 extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, uint64_t seed, RsSim** out) {
@@ -770,7 +817,7 @@ extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, ui
   TRY(dev_dup(s, d.origin_rate, sc->n_origins)); TRY(dev_dup(s, d.origin_route_off, sc->n_origins + 1));
   TRY(dev_dup(s, d.origin_route, sc->n_origin_routes));
   TRY(dev_dup(s, d.origin_watch_off, sc->n_origins + 1)); TRY(dev_dup(s, d.origin_watch_lane, sc->n_watch));
-  TRY(dev_dup(s, d.origin_watch_dist, sc->n_watch));
+  TRY(dev_dup(s, d.origin_watch_dist, sc->n_watch)); TRY(dev_dup(s, d.origin_watch_owner, sc->n_watch));
   const size_t N = (size_t)n_env;
   TRY(dev_alloc(s, s->d.hdr, N * kHdrInts));
   TRY(dev_alloc(s, s->d.tls_phase, N * sc->n_tls)); TRY(dev_alloc(s, s->d.tls_end, N * sc->n_tls));
@@ -800,6 +847,14 @@ extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, ui
   }
   const char* eb = getenv("RESCO_B200_BLOCK");
   s->block = eb ? atoi(eb) : 128;
+  const char* er = getenv("RESCO_B200_REGCAP");
+  s->minb = (er ? atoi(er) != 0 : true) ? 1024 / s->block : 1;   // default: 64 registers/thread for occupancy
+  const char* ep = getenv("RESCO_B200_PERSIST");
+  s->d.persistent = ep ? atoi(ep) : 1;
+  s->n_sm = prop.multiProcessorCount;
+  TRY(dev_alloc(s, s->d.work_counter, 1));
+  const char* ec = getenv("RESCO_B200_CARVEOUT");
+  s->carveout = ec ? atoi(ec) : -1;
   TRY(configure(s));
   CK(cudaEventCreate(&s->ev0)); CK(cudaEventCreate(&s->ev1));
   *out = s;
@@ -886,10 +941,10 @@ extern "C" int rs_policy_maxpressure(RsSim* s, const int32_t* h_pairs, int32_t n
   const int S = s->d.sc.n_signals;
   if (s->n_pairs_alloc != n_pairs) {
     TRY(dev_alloc(s, s->d_pairs, (size_t)n_pairs * 2));
-    TRY(dev_alloc(s, s->d_valid, (size_t)n_pairs * S));
+    TRY(dev_alloc(s, s->d_valid, (size_t)n_pairs * S * 2));
     s->n_pairs_alloc = n_pairs;
     CK(cudaMemcpy(s->d_pairs, h_pairs, sizeof(int32_t) * n_pairs * 2, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(s->d_valid, h_valid, sizeof(int32_t) * n_pairs * S, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s->d_valid, h_valid, sizeof(int32_t) * n_pairs * S * 2, cudaMemcpyHostToDevice));
   }
   int total = s->d.n_env * S;
   int32_t* outp = d_actions_out ? d_actions_out : s->d_actions;

@@ -17,6 +17,15 @@
 
 #include "../../include/resco_b200.h"
 
+#ifndef RS_INLINE_HEAVY
+#define RS_INLINE_HEAVY 1
+#endif
+#if RS_INLINE_HEAVY
+#define RS_HEAVY __device__ __forceinline__
+#else
+#define RS_HEAVY __device__ __noinline__
+#endif
+
 namespace rs {
 
 constexpr int kMaxHops = 8;
@@ -53,6 +62,8 @@ struct DevSim {
   int32_t* phase_obs;     // [N][S]
   float *mplight, *wave, *rew_wait, *rew_wait_norm, *rew_pressure;
   int32_t *sig_queue_len, *sig_max_queue;
+  int32_t* work_counter;  // dynamic instance scheduler of the persistent launch
+  int32_t persistent;
 };
 
 struct RunArgs {
@@ -149,6 +160,16 @@ __device__ __forceinline__ int v_route(const Tile& t, int i) { return (int)(t.rc
 __device__ __forceinline__ int v_cursor(const Tile& t, int i) { return (int)(t.rc[i] >> 16); }
 __device__ __forceinline__ int v_wait(const Tile& t, int i) { return (int)(t.wr[i] & 0xFFFFu); }
 __device__ __forceinline__ int v_lane(const Tile& t, int i) { return (int)(t.dl[i] >> 16); }
+// cached choose_link() of the vehicle's CURRENT lane (meta bits 24..31: index relative to the lane's
+// first link, 0xFE = route ends here (-1), 0xFD = lane does not lead on (-2)); refreshed whenever the
+// vehicle enters a lane, so that the plan phase and the foe checks read it with one LDS.
+__device__ __forceinline__ uint32_t encode_nextlink(const RsScenario& sc, int lane, int k) {
+  return k == -1 ? 0xFEu : (k < 0 ? 0xFDu : (uint32_t)(k - __ldg(sc.lane_link_off + lane)));
+}
+__device__ __forceinline__ int v_nextlink(const RsScenario& sc, const Tile& t, int i, int lane) {
+  uint32_t r = t.meta[i] >> 24;
+  return r == 0xFEu ? -1 : (r == 0xFDu ? -2 : __ldg(sc.lane_link_off + lane) + (int)r);
+}
 __device__ __forceinline__ int lane_count(const Tile& t, int l) { return (int)t.lane_start[l + 1] - (int)t.lane_start[l]; }
 
 __device__ __forceinline__ void rng4(const Tile& t, uint32_t stream, uint32_t a, uint32_t b, uint32_t out[4]) {
@@ -169,7 +190,7 @@ __device__ __forceinline__ float speed_factor(const Tile& t, int32_t vid, float 
 }
 
 // which link does a vehicle with (route, cursor) take at the end of `lane`?  -1: route ends, -2: wrong lane
-__device__ __forceinline__ int choose_link(const RsScenario& sc, int lane, int route, int cursor) {
+RS_HEAVY int choose_link(const RsScenario& sc, int lane, int route, int cursor) {
   int k0 = __ldg(sc.lane_link_off + lane), k1 = __ldg(sc.lane_link_off + lane + 1);
   if (__ldg(sc.lane_internal + lane)) return k0 < k1 ? k0 : -2;
   int ro = __ldg(sc.route_off + route), rn = __ldg(sc.route_off + route + 1) - ro;
@@ -200,7 +221,7 @@ __device__ __forceinline__ bool time_conflict(float seen, float v, float cross, 
 }
 
 // right-of-way: must the vehicle on entry link k wait for one of its foes?
-__device__ bool link_blocked(const RsScenario& sc, const Tile& t, int k, float seen, float v, float cross) {
+RS_HEAVY bool link_blocked(const RsScenario& sc, const Tile& t, int k, float seen, float v, float cross) {
   int f0 = __ldg(sc.link_foe_off + k), f1 = __ldg(sc.link_foe_off + k + 1);
   for (int fi = f0; fi < f1; ++fi) {
     int f = __ldg(sc.foe_link + fi), fl = __ldg(sc.foe_flags + fi);
@@ -210,7 +231,7 @@ __device__ bool link_blocked(const RsScenario& sc, const Tile& t, int k, float s
     int a0 = __ldg(sc.link_from + f);
     if (lane_count(t, a0) > 0) {
       int h = t.lane_start[a0];
-      if (choose_link(sc, a0, v_route(t, h), v_cursor(t, h)) == f) {
+      if (v_nextlink(sc, t, h, a0) == f) {
         float dist_f = __ldg(sc.lane_len + a0) - t.pos[h];
         int fst = state_now(sc, t, f);
         bool goes = true;
@@ -247,7 +268,7 @@ __device__ __forceinline__ float lane_occ(const Tile& t, int l) {
 }
 
 // stop-line decision for link k, `seen` metres ahead of vehicle i (hop 0 = the link at the end of its lane)
-__device__ bool must_stop(const RsScenario& sc, const Tile& t, int i, int k, float seen, int hop, int cursor) {
+RS_HEAVY bool must_stop(const RsScenario& sc, const Tile& t, int i, int k, float seen, int hop, int cursor) {
   int vt = v_vtype(t, i);
   float len = VTT(t, vt, VT_LEN), decel = VTT(t, vt, VT_DECEL);
   float v = t.speed[i];
@@ -311,7 +332,7 @@ __device__ __forceinline__ int strategic_dir(const RsScenario& sc, int route, in
 
 // Plan one vehicle from the state at the start of the tick: next speed + lane it will be in
 // laterally (own lane unless a lane change / head swap was decided).
-__device__ void plan_vehicle(const RsScenario& sc, const Tile& t, int i, float& vn_out, int& target_out) {
+RS_HEAVY void plan_vehicle(const RsScenario& sc, const Tile& t, int i, float& vn_out, int& target_out) {
   int lane = v_lane(t, i);
   int rank = i - (int)t.lane_start[lane];
   int vt = v_vtype(t, i);
@@ -336,7 +357,7 @@ __device__ void plan_vehicle(const RsScenario& sc, const Tile& t, int i, float& 
     int cur = lane, cc = cursor;
     float la = brake_gap(vacc, decel, 0.0f) + 2.0f * vacc + 5.0f;
     for (int hop = 0; hop < kMaxHops; ++hop) {
-      int k = choose_link(sc, cur, route, cc);
+      int k = hop == 0 ? v_nextlink(sc, t, i, lane) : choose_link(sc, cur, route, cc);
       if (k == -1) break;
       if (k == -2) {
         vsafe = fminf(vsafe, max_safe_stop_speed(seen, decel, tau));
@@ -430,7 +451,7 @@ __device__ void plan_vehicle(const RsScenario& sc, const Tile& t, int i, float& 
       int y = t.lane_start[nl];
       if (t.speed[y] < kHaltSpeed && __ldg(sc.lane_len + nl) - t.pos[y] < 1.0f &&
           (__ldg(sc.lane_perm + lane) & __ldg(sc.vtype_bit + v_vtype(t, y))) &&
-          choose_link(sc, nl, v_route(t, y), v_cursor(t, y)) == -2 &&
+          v_nextlink(sc, t, y, nl) == -2 &&
           strategic_dir(sc, v_route(t, y), v_cursor(t, y), nl) == -d) {
         target = nl;
         vn = 0.0f;

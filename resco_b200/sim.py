@@ -18,7 +18,7 @@ from .abi import Marshalled, RsObsView, RsScenario, RsStats, STATS_DTYPE
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(_CSRC, "libresco_b200.so")
+LIB_PATH = os.environ.get("RESCO_B200_LIB", os.path.join(_CSRC, "libresco_b200.so"))
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
@@ -176,13 +176,14 @@ class VecSim:
         if self._policy_tables is None:
             npairs = len(pairs)
             pr = np.ascontiguousarray(np.asarray(pairs, np.int32).reshape(-1))
-            va = np.full((self.S, npairs), -1, np.int32)
+            va = np.full((self.S, npairs, 2), -1, np.int32)
             for i, s in enumerate(signal_ids):
                 if valid_acts is None:
-                    va[i, :] = np.arange(npairs)
+                    va[i, :, 0] = np.arange(npairs)
+                    va[i, :, 1] = np.arange(npairs)
                 else:
-                    for k, v in valid_acts[s].items():
-                        va[i, int(k)] = int(v)
+                    for k, (pair_idx, action) in enumerate(valid_acts[s].items()):   # dict order == evaluation order
+                        va[i, k] = (int(pair_idx), int(action))
             self._policy_tables = (pr, np.ascontiguousarray(va), npairs)
             self._policy_out = t.zeros((self.n_env, self.S), dtype=t.int32, device=f"cuda:{self.device}")
         pr, va, npairs = self._policy_tables
