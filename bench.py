@@ -39,12 +39,17 @@ N_ENV_PER_GPU = 4096
 VCAP = 128   # cologne8/MaxPressure peaks at ~110 concurrent vehicles per instance (32-seed CPU check); a full tile only delays insertions
 
 
-def _marshal(map_name=MAP, vcap=VCAP):
+def _marshal(map_name=MAP, vcap=VCAP, synthetic_rate=0.0):
     from resco_b200.abi import marshal
     from resco_b200.scenario import Scenario
     sc = Scenario.load(os.path.join(ROOT, "resco_b200", "data", map_name + ".npz"))
     mc = sc.meta["map_config"]
-    m = marshal(sc, step_length=mc["step_length"], yellow_length=mc["yellow_length"], max_distance=200.0, vcap=vcap)
+    synth = None
+    if synthetic_rate > 0:
+        from resco_b200.scenario.synth import synth_demand
+        synth = synth_demand(sc, synthetic_rate)
+    m = marshal(sc, step_length=mc["step_length"], yellow_length=mc["yellow_length"], max_distance=200.0, vcap=vcap,
+                synthetic=synth)
     return sc, m
 
 
@@ -170,7 +175,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     if not os.path.exists(os.path.join(ROOT, "resco_b200", "csrc", "libresco_b200.so")):
         build_library()
-    sc, m = _marshal(args.map, args.vcap)
+    sc, m = _marshal(args.map, args.vcap, args.synthetic_rate)
     n_env = args.n_env
     sim = VecSim(m, n_env, seed=args.seed, device=local)
     sim.reset(args.seed, rank * n_env)
@@ -288,7 +293,8 @@ def run_ours(args):
             "metric": "env steps/sec (summed instances)", "value": value, "unit": "env steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.map} (8 signals) / MaxPressure / {n_env} lock-step instances per GPU",
+            "config": {"workload": f"{args.map} ({sim.S} signals) / MaxPressure / {n_env} lock-step instances per GPU"
+                                   + (f" / synthetic Bernoulli demand {args.synthetic_rate:g} veh/h/entry-lane" if args.synthetic_rate > 0 else ""),
                        "n_env_per_gpu": n_env, "n_env_total": total_env, "sim_ticks_per_env_step": m.struct.step_length,
                        "vcap": m.struct.vcap, "block_threads": int(os.environ.get("RESCO_B200_BLOCK", "128")), "regs_per_thread": 64 if os.environ.get("RESCO_B200_REGCAP", "1") != "0" else "uncapped", "persistent_grid": os.environ.get("RESCO_B200_PERSIST", "1") != "0",
                        "l2": "flushed between timed steps (256 MiB memset, untimed)",
@@ -344,6 +350,7 @@ def main():
     ap.add_argument("--vcap", type=int, default=VCAP)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--preroll", type=int, default=90, help="untimed env steps after reset before warm-up")
+    ap.add_argument("--synthetic-rate", type=float, default=0.0, help="veh/h per entry lane (configs[4]); 0 = map's trip table")
     ap.add_argument("--allgather", action="store_true", help="NCCL all-gather of the mplight obs every step (C4)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -243,6 +243,17 @@ def marshal(sc: Scenario, *, step_length: int = 10, yellow_length: int = 3, max_
         sizes["n_origin_routes"] = len(synthetic["origin_route"])
         sizes["n_trips"] = 0
         arrays["origin_off"] = (np.zeros(sizes["n_origins"] + 1, np.int32), np.int32)
+        if "route_off" in synthetic:     # the synthetic demand brings its own route / vType tables
+            for nm in ("route_off", "route_edge", "route_mask", "vtype_bit"):
+                arrays[nm] = (synthetic[nm], np.int32)
+            arrays["vtype"] = (synthetic["vtype_table"], np.float32)
+            sizes["n_routes"] = len(synthetic["route_off"]) - 1
+            sizes["n_route_steps"] = len(synthetic["route_edge"])
+            sizes["n_vtypes"] = len(synthetic["vtype_bit"])
+        for nm in ("trip_depart",):
+            arrays[nm] = (np.zeros(1, np.float32), np.float32)
+        for nm in ("trip_route", "trip_vtype", "trip_file"):
+            arrays[nm] = (np.zeros(1, np.int32), np.int32)
     for k, v in sizes.items():
         setattr(st, k, int(v))
     for name, ct in _PTRS:

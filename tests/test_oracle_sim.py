@@ -107,3 +107,29 @@ def test_yellow_then_green_schedule():
     o2.reset(0, 0)
     o2.env_step(act)
     assert o2.phases(0)[0] == 1 or m.info["programs_installed"][sig][1][0] <= 7
+
+
+def test_synthetic_poisson_demand_grid():
+    """BASELINE configs[4]: synthetic 4x4 grid, Bernoulli-per-tick arrivals per entry lane."""
+    from resco_b200.abi import marshal
+    from resco_b200.scenario.synth import synth_demand
+    sc = util.load("grid4x4")
+    inserted = []
+    for rate in (300, 1200):
+        sy = synth_demand(sc, rate)
+        assert sy["n_entry_lanes"] >= 40 and (np.diff(sy["origin_route_off"]) > 0).all()
+        m = marshal(sc, step_length=10, yellow_length=3, synthetic=sy, vcap=512)
+        o = OracleSim(m, 2, seed=3)
+        o.reset(3, 0)
+        o.observe()
+        for step in range(30):
+            o.env_step(util.cyclic_actions(m, 2, step))
+        st = o.stats()
+        assert (st["anomalies"] == 0).all()
+        assert (st["n_inserted"] == st["n_arrived"] + st["n_active"]).all()
+        assert (st["n_active"] <= 512).all()
+        inserted.append(int(st["n_inserted"][0] + st["n_backlog"][0]))      # total requests so far
+        a, b = o.vehicles(0), o.vehicles(1)
+        assert not np.array_equal(a["vid"][:20], b["vid"][:20]) or not np.array_equal(a["pos"][:20], b["pos"][:20])
+    # request rate scales with lambda: 300 s * 40+ lanes * p
+    assert 0.6 * 4 < inserted[1] / max(inserted[0], 1) < 1.4 * 4
