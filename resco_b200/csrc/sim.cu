@@ -63,7 +63,7 @@ struct OriginCand { int32_t route, vt, vid, ok_dd, unsafe; };   // ok_dd: -1 not
 
 // ------------------------------------------------------------------------------------------------
 template <int BLOCK>
-__device__ void tick_body(const DevSim& D, const SmemLayout& m, unsigned char* smem, Tile& T, uint32_t*& cur,
+__device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, unsigned char* smem, Tile& T, uint32_t*& cur,
                           uint32_t*& oth) {
   const RsScenario& sc = D.sc;
   const int tid = threadIdx.x;
@@ -373,7 +373,7 @@ __device__ void tick_body(const DevSim& D, const SmemLayout& m, unsigned char* s
 // ------------------------------------------------------------------------------------------------
 // Signal.observe (traffic_signal.py:189-235) + states.mplight / wave + rewards.* + calc_metrics
 template <int BLOCK>
-__device__ void observe_body(const DevSim& D, const SmemLayout& m, unsigned char* smem, Tile& T, int env) {
+__device__ __forceinline__ void observe_body(const DevSim& D, const SmemLayout& m, unsigned char* smem, Tile& T, int env) {
   const RsScenario& sc = D.sc;
   const int tid = threadIdx.x, lane_id = tid & 31, wid = tid >> 5, nw = BLOCK / 32;
   int32_t* hdr = (int32_t*)(smem + m.off_hdr);
@@ -575,17 +575,20 @@ __device__ __forceinline__ void run_instance(const DevSim& D, const RunArgs& A, 
 // CTA pulls the next environment instance from a global counter until all N are stepped, so there
 // is no partial last wave and uneven instances balance out.
 template <int BLOCK, int MINB>
-__global__ void __launch_bounds__(BLOCK, MINB) k_run(DevSim D, RunArgs A) {
+__global__ void __launch_bounds__(BLOCK, MINB) k_run(const __grid_constant__ DevSim D, const __grid_constant__ RunArgs A) {
   extern __shared__ __align__(16) unsigned char smem[];
   const SmemLayout m = make_layout(D.sc);
-  if (!D.persistent) { run_instance<BLOCK>(D, A, m, smem, blockIdx.x); return; }
   __shared__ int s_env;
+#pragma unroll 1
   for (;;) {
-    if (threadIdx.x == 0) s_env = atomicAdd(D.work_counter, 1);
-    __syncthreads();
-    const int env = s_env;
+    if (D.persistent) {
+      if (threadIdx.x == 0) s_env = atomicAdd(D.work_counter, 1);
+      __syncthreads();
+    }
+    const int env = D.persistent ? s_env : (int)blockIdx.x;
     if (env >= D.n_env) break;
     run_instance<BLOCK>(D, A, m, smem, env);
+    if (!D.persistent) break;
     __syncthreads();
   }
 }

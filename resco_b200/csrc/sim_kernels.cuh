@@ -190,7 +190,7 @@ __device__ __forceinline__ float speed_factor(const Tile& t, int32_t vid, float 
 }
 
 // which link does a vehicle with (route, cursor) take at the end of `lane`?  -1: route ends, -2: wrong lane
-RS_HEAVY int choose_link(const RsScenario& sc, int lane, int route, int cursor) {
+__device__ __noinline__ int choose_link(const RsScenario& sc, int lane, int route, int cursor) {
   int k0 = __ldg(sc.lane_link_off + lane), k1 = __ldg(sc.lane_link_off + lane + 1);
   if (__ldg(sc.lane_internal + lane)) return k0 < k1 ? k0 : -2;
   int ro = __ldg(sc.route_off + route), rn = __ldg(sc.route_off + route + 1) - ro;
@@ -273,23 +273,32 @@ RS_HEAVY bool must_stop(const RsScenario& sc, const Tile& t, int i, int k, float
   float len = VTT(t, vt, VT_LEN), decel = VTT(t, vt, VT_DECEL);
   float v = t.speed[i];
   int from = __ldg(sc.link_from + k);
-  if (__ldg(sc.lane_internal + from)) {
+  const bool from_internal = __ldg(sc.lane_internal + from) != 0;
+  int yield_link = -1;          // entry link whose foes must be checked (one call site for link_blocked)
+  float cross = 0.0f;
+  int st = 0;
+  if (from_internal) {
     int p = __ldg(sc.link_parent + k);
-    if (hop == 0 && p >= 0 && __ldg(sc.link_cont + p) && __ldg(sc.link_via + p) == from)
-      return link_blocked(sc, t, p, seen, v, __ldg(sc.link_via_len + p) - __ldg(sc.lane_len + from) + len);
-    return false;
+    if (!(hop == 0 && p >= 0 && __ldg(sc.link_cont + p) && __ldg(sc.link_via + p) == from)) return false;
+    yield_link = p;
+    cross = __ldg(sc.link_via_len + p) - __ldg(sc.lane_len + from) + len;
+  } else {
+    st = state_now(sc, t, k);
+    if (st == 'r' || st == 'u') return true;
+    if (st == 'y' || st == 'Y') return seen >= brake_gap(v, decel, 0.0f);
+    if (st == 's' && !(v_wait(t, i) > 0 && seen <= 2.0f)) return true;
+    if (hop != 0) return false;
+    bool minor = (st == 'g' || st == 'm' || st == '=' || st == 'Z' || st == 'w' || st == 's' || st == 'o');
+    if (!__ldg(sc.link_cont + k) && minor) { yield_link = k; cross = __ldg(sc.link_via_len + k) + len; }
   }
-  int st = state_now(sc, t, k);
-  if (st == 'r' || st == 'u') return true;
-  if (st == 'y' || st == 'Y') return seen >= brake_gap(v, decel, 0.0f);
-  if (st == 's' && !(v_wait(t, i) > 0 && seen <= 2.0f)) return true;
-  if (hop != 0) return false;
-  bool minor = (st == 'g' || st == 'm' || st == '=' || st == 'Z' || st == 'w' || st == 's' || st == 'o');
+  if (yield_link >= 0) {
+    bool b = link_blocked(sc, t, yield_link, seen, v, cross);
+    if (from_internal) return b;
+    if (b) return true;
+  }
   if (__ldg(sc.link_cont + k)) {
     if (lane_count(t, __ldg(sc.link_via + k)) > 0) return true;   // waiting slot inside the junction is taken
-  } else if (minor) {
-    if (link_blocked(sc, t, k, seen, v, __ldg(sc.link_via_len + k) + len)) return true;
-  } else {
+  } else if (yield_link < 0) {
     int f0 = __ldg(sc.link_foe_off + k), f1 = __ldg(sc.link_foe_off + k + 1);
     for (int fi = f0; fi < f1; ++fi) {
       int li = __ldg(sc.link_last_int + __ldg(sc.foe_link + fi));
