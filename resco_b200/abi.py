@@ -298,6 +298,7 @@ def smem_bytes(vcap: int, n_lanes: int, n_tls: int, n_signals: int, n_origins: i
     o = al(o + n_lanes * 4)
     o = al(o + n_tls * 4)
     o = al(o + n_tls * 4)
+    o = al(o + n_tls * 4)
     o = al(o + max(n_signals, 1) * 4)
     o = al(o + max(n_origins, 1) * 4)
     o = al(o + max(n_origins, 1) * 4)

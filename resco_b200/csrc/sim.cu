@@ -19,7 +19,7 @@ struct SmemLayout {
   int vcap, L, n_tls, S, O, SL, n_vt;
   size_t off_bufA, off_bufB, off_vn, off_newlane, off_newidx, off_mnext, off_arr;
   size_t off_lane_start, off_start2, off_cnt2, off_mhead;
-  size_t off_tls_phase, off_tls_end, off_next_phase, off_origin_cur, off_origin_backlog, off_origin_cand;
+  size_t off_tls_phase, off_tls_end, off_tls_state, off_next_phase, off_origin_cur, off_origin_backlog, off_origin_cand;
   size_t off_vt, off_hdr, off_misc, off_obs;
   size_t total;
 };
@@ -44,6 +44,7 @@ __host__ __device__ inline SmemLayout make_layout(const RsScenario& sc) {
   m.off_mhead = o; o = align16(o + (size_t)m.L * 4);
   m.off_tls_phase = o; o = align16(o + (size_t)m.n_tls * 4);
   m.off_tls_end = o; o = align16(o + (size_t)m.n_tls * 4);
+  m.off_tls_state = o; o = align16(o + (size_t)m.n_tls * 4);
   m.off_next_phase = o; o = align16(o + (size_t)(m.S > 0 ? m.S : 1) * 4);
   m.off_origin_cur = o; o = align16(o + (size_t)(m.O > 0 ? m.O : 1) * 4);
   m.off_origin_backlog = o; o = align16(o + (size_t)(m.O > 0 ? m.O : 1) * 4);
@@ -66,7 +67,7 @@ template <int BLOCK>
 __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, unsigned char* smem, Tile& T, uint32_t*& cur,
                           uint32_t*& oth) {
   const RsScenario& sc = D.sc;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x % BLOCK;   // BLOCK = threads per instance (a CTA may hold several instances)
   const int L = m.L;
   float* vn = (float*)(smem + m.off_vn);
   uint16_t* newlane = (uint16_t*)(smem + m.off_newlane);
@@ -93,6 +94,7 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
       int d = __ldg(sc.phase_dur + p0 + ph);
       T.tls_end[t] += d > 0 ? d : 1;
     }
+    T.tls_state[t] = __ldg(sc.phase_state_off + p0 + T.tls_phase[t]);
   }
   for (int l = tid; l < L; l += BLOCK) { cnt2[l] = lane_count(T, l); mhead[l] = -1; }
   if (tid == 0) { misc[M_NARR] = 0; misc[M_NOK] = 0; }
@@ -375,7 +377,7 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
 template <int BLOCK>
 __device__ __forceinline__ void observe_body(const DevSim& D, const SmemLayout& m, unsigned char* smem, Tile& T, int env) {
   const RsScenario& sc = D.sc;
-  const int tid = threadIdx.x, lane_id = tid & 31, wid = tid >> 5, nw = BLOCK / 32;
+  const int tid = threadIdx.x % BLOCK, lane_id = tid & 31, wid = tid >> 5, nw = BLOCK / 32;
   int32_t* hdr = (int32_t*)(smem + m.off_hdr);
   float* ob = (float*)(smem + m.off_obs);   // [5][SL]
   const int SL = m.SL, S = m.S;
@@ -462,13 +464,14 @@ __device__ __forceinline__ void dev_set_phase(const RsScenario& sc, Tile& T, int
   if (idx < 0 || idx >= np) return;
   T.tls_phase[t] = idx;
   T.tls_end[t] = T.tick + __ldg(sc.phase_dur + p0 + idx);
+  T.tls_state[t] = __ldg(sc.phase_state_off + p0 + idx);
 }
 
 template <int BLOCK>
 __device__ __forceinline__ void run_instance(const DevSim& D, const RunArgs& A, const SmemLayout& m,
                                              unsigned char* smem, const int env) {
   const RsScenario& sc = D.sc;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x % BLOCK;
   uint32_t* cur = (uint32_t*)(smem + m.off_bufA);
   uint32_t* oth = (uint32_t*)(smem + m.off_bufB);
   int32_t* hdr = (int32_t*)(smem + m.off_hdr);
@@ -481,6 +484,7 @@ __device__ __forceinline__ void run_instance(const DevSim& D, const RunArgs& A, 
   T.lane_start = (uint16_t*)(smem + m.off_lane_start);
   T.tls_phase = (int32_t*)(smem + m.off_tls_phase);
   T.tls_end = (int32_t*)(smem + m.off_tls_end);
+  T.tls_state = (int32_t*)(smem + m.off_tls_state);
   T.vt = vt;
   const uint64_t env_id = (uint64_t)(D.first_env_id + env);
   T.env_lo = (uint32_t)env_id; T.env_hi = (uint32_t)(env_id >> 32);
@@ -571,23 +575,26 @@ __device__ __forceinline__ void run_instance(const DevSim& D, const RunArgs& A, 
   }
 }
 
-// Persistent launch: the grid holds as many CTAs as are resident at once (148 SMs x CTAs/SM); each
-// CTA pulls the next environment instance from a global counter until all N are stepped, so there
-// is no partial last wave and uneven instances balance out.
-template <int BLOCK, int MINB>
-__global__ void __launch_bounds__(BLOCK, MINB) k_run(const __grid_constant__ DevSim D, const __grid_constant__ RunArgs A) {
+// Persistent launch: the grid holds as many CTAs as are resident at once (148 SMs x CTAs/SM); each CTA
+// steps G instances in lock-step (TPI threads each: one instruction stream and one set of barriers serve
+// G instances, which keeps the instruction cache and the warp slots busy) and pulls the next G from a
+// global counter until all N are done -- no partial last wave, uneven instances balance out.
+template <int TPI, int G, int MINB>
+__global__ void __launch_bounds__(TPI * G, MINB) k_run(const __grid_constant__ DevSim D, const __grid_constant__ RunArgs A) {
   extern __shared__ __align__(16) unsigned char smem[];
   const SmemLayout m = make_layout(D.sc);
+  unsigned char* my = smem + (size_t)(threadIdx.x / TPI) * m.total;
   __shared__ int s_env;
 #pragma unroll 1
   for (;;) {
     if (D.persistent) {
-      if (threadIdx.x == 0) s_env = atomicAdd(D.work_counter, 1);
+      if (threadIdx.x == 0) s_env = atomicAdd(D.work_counter, G);
       __syncthreads();
     }
-    const int env = D.persistent ? s_env : (int)blockIdx.x;
-    if (env >= D.n_env) break;
-    run_instance<BLOCK>(D, A, m, smem, env);
+    const int env0 = D.persistent ? s_env : (int)blockIdx.x * G;
+    if (env0 >= D.n_env) break;
+    // a slot past the end of the batch repeats the last instance (same inputs -> identical stores)
+    run_instance<TPI>(D, A, m, my, min(env0 + (int)(threadIdx.x / TPI), D.n_env - 1));
     if (!D.persistent) break;
     __syncthreads();
   }
@@ -688,7 +695,8 @@ struct RsSim {
   DevSim d;
   SmemLayout layout;
   int device;
-  int block;
+  int block;   // threads per instance
+  int group;   // instances per CTA
   int minb;
   int carveout;
   int n_sm;
@@ -735,41 +743,43 @@ static int dev_alloc(RsSim* s, T*& out, size_t count) {
 }
 #define TRY(x) do { int _r = (x); if (_r) return _r; } while (0)
 
-template <int BLOCK, int MINB>
+template <int TPI, int G, int MINB>
 static int launch_run(RsSim* s, const RunArgs& a, cudaStream_t st) {
-  int grid = s->d.n_env;
+  int grid = (s->d.n_env + G - 1) / G;
   if (s->d.persistent) {
     CK(cudaMemsetAsync(s->d.work_counter, 0, sizeof(int32_t), st));
     if (s->resident_ctas < grid) grid = s->resident_ctas;
   }
-  k_run<BLOCK, MINB><<<grid, BLOCK, s->layout.total, st>>>(s->d, a);
+  k_run<TPI, G, MINB><<<grid, TPI * G, (size_t)s->layout.total * G, st>>>(s->d, a);
   s->launches += 1;
   CK(cudaGetLastError());
   return 0;
 }
 
-// variant = block threads * 10 + (1 if registers are capped at 64/thread for occupancy)
-#define RS_VARIANTS(X) X(32, 1) X(32, 32) X(64, 1) X(64, 16) X(128, 1) X(128, 8) X(256, 1) X(256, 4)
+// (threads per instance, instances per CTA, min CTAs/SM for __launch_bounds__: 1 = registers uncapped,
+//  1024/(TPI*G) = 64 registers per thread)
+#define RS_VARIANTS(X) X(32, 1, 1) X(32, 1, 32) X(32, 4, 8) X(64, 1, 1) X(64, 1, 16) X(64, 2, 1) X(64, 2, 8) X(64, 4, 1) \
+  X(64, 4, 4) X(64, 6, 1) X(64, 8, 2) X(64, 8, 1) X(64, 9, 1) X(32, 16, 1) X(32, 8, 1) X(128, 4, 1) X(128, 1, 1) X(128, 1, 8) X(128, 2, 1) X(128, 2, 4) X(128, 4, 2) X(256, 1, 1) X(256, 1, 4)
 
 static int run(RsSim* s, const RunArgs& a, cudaStream_t st) {
-#define X(B, M) if (s->block == B && s->minb == M) return launch_run<B, M>(s, a, st);
+#define X(B, G, M) if (s->block == B && s->group == G && s->minb == M) return launch_run<B, G, M>(s, a, st);
   RS_VARIANTS(X)
 #undef X
-  return fail(RS_ERR_INVALID, "unsupported RESCO_B200_BLOCK / RESCO_B200_REGCAP combination");
+  return fail(RS_ERR_INVALID, "unsupported RESCO_B200_BLOCK / RESCO_B200_GROUP / RESCO_B200_REGCAP combination");
 }
 
 static int configure(RsSim* s) {
-  const int bytes = (int)s->layout.total;
-#define X(B, M) if (s->block == B && s->minb == M) { \
-    CK(cudaFuncSetAttribute(k_run<B, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); \
-    if (s->carveout >= 0) CK(cudaFuncSetAttribute(k_run<B, M>, cudaFuncAttributePreferredSharedMemoryCarveout, s->carveout)); \
+  const int bytes = (int)s->layout.total * s->group;
+#define X(B, G, M) if (s->block == B && s->group == G && s->minb == M) { \
+    CK(cudaFuncSetAttribute(k_run<B, G, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); \
+    if (s->carveout >= 0) CK(cudaFuncSetAttribute(k_run<B, G, M>, cudaFuncAttributePreferredSharedMemoryCarveout, s->carveout)); \
     int per_sm = 0; \
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_run<B, M>, B, bytes)); \
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_run<B, G, M>, B * G, bytes)); \
     s->resident_ctas = (per_sm > 0 ? per_sm : 1) * s->n_sm; \
     return 0; }
   RS_VARIANTS(X)
 #undef X
-  return fail(RS_ERR_INVALID, "RESCO_B200_BLOCK must be 32/64/128/256 (RESCO_B200_REGCAP 0/1)");
+  return fail(RS_ERR_INVALID, "unsupported RESCO_B200_BLOCK / RESCO_B200_GROUP / RESCO_B200_REGCAP combination");
 }
 
 extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, uint64_t seed, RsSim** out) {
@@ -849,9 +859,13 @@ extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, ui
     return fail(RS_ERR_CAPACITY, buf);
   }
   const char* eb = getenv("RESCO_B200_BLOCK");
-  s->block = eb ? atoi(eb) : 128;
+  s->block = eb ? atoi(eb) : 64;
   const char* er = getenv("RESCO_B200_REGCAP");
-  s->minb = (er ? atoi(er) != 0 : true) ? 1024 / s->block : 1;   // default: 64 registers/thread for occupancy
+  const char* eg = getenv("RESCO_B200_GROUP");
+  s->group = eg ? atoi(eg) : 8;
+  while (s->group > 1 && (size_t)s->layout.total * s->group > (size_t)prop.sharedMemPerBlockOptin)
+    s->group = s->group > 8 ? 8 : (s->group == 6 ? 4 : s->group / 2);   // largest compiled shape that fits
+  s->minb = (er ? atoi(er) != 0 : false) ? 1024 / (s->block * s->group) : 1;   // default: registers uncapped
   const char* ep = getenv("RESCO_B200_PERSIST");
   s->d.persistent = ep ? atoi(ep) : 1;
   s->n_sm = prop.multiProcessorCount;

@@ -142,6 +142,7 @@ struct Tile {
   uint32_t* dl;    // depart delay (lo16) | lane (hi16)
   uint16_t* lane_start;   // [L+1]
   int32_t* tls_phase; int32_t* tls_end;
+  int32_t* tls_state;     // [n_tls] offset into state_chars of the phase currently shown
   const float* vt;        // vtype table in smem
   int32_t tick;
   uint32_t env_lo, env_hi, seed_lo, seed_hi;
@@ -209,8 +210,8 @@ __device__ __noinline__ int choose_link(const RsScenario& sc, int lane, int rout
 __device__ __forceinline__ int state_now(const RsScenario& sc, const Tile& t, int k) {
   int tl = __ldg(sc.link_tls + k);
   if (tl < 0) return __ldg(sc.link_state + k);
-  int p = __ldg(sc.tls_phase_off + tl) + t.tls_phase[tl];
-  return (int)__ldg(sc.state_chars + __ldg(sc.phase_state_off + p) + __ldg(sc.link_tlidx + k));
+  // tls_state[tl] = offset of the current phase's state string (refreshed in shared memory whenever a phase changes)
+  return (int)__ldg(sc.state_chars + t.tls_state[tl] + __ldg(sc.link_tlidx + k));
 }
 
 __device__ __forceinline__ bool time_conflict(float seen, float v, float cross, float dist_f, float v_f, float cross_f) {
@@ -475,7 +476,7 @@ RS_HEAVY void plan_vehicle(const RsScenario& sc, const Tile& t, int i, float& vn
 // block-wide exclusive prefix sum over `n` ints in shared memory (in: cnt, out: start u16[n+1])
 template <int BLOCK>
 __device__ void block_prefix(const int32_t* cnt, uint16_t* start, int n, int32_t* warp_tot) {
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int tid = threadIdx.x % BLOCK, lane = tid & 31, wid = tid >> 5;   // BLOCK = threads per instance
   const int per = (n + BLOCK - 1) / BLOCK;
   const int a = min(tid * per, n), b = min(a + per, n);
   int s = 0;
