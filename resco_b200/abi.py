@@ -307,6 +307,7 @@ def smem_bytes(vcap: int, n_lanes: int, n_tls: int, n_signals: int, n_origins: i
     o = al(o + 16 * 4)
     o = al(o + 64 * 4)
     o = al(o + max(n_sig_lanes, 1) * 20)
+    o = al(o + 16)
     return o
 
 

@@ -20,7 +20,7 @@ struct SmemLayout {
   size_t off_bufA, off_bufB, off_vn, off_newlane, off_newidx, off_mnext, off_arr;
   size_t off_lane_start, off_start2, off_cnt2, off_mhead;
   size_t off_tls_phase, off_tls_end, off_tls_state, off_next_phase, off_origin_cur, off_origin_backlog, off_origin_cand;
-  size_t off_vt, off_hdr, off_misc, off_obs;
+  size_t off_vt, off_hdr, off_misc, off_obs, off_mbar;
   size_t total;
 };
 
@@ -53,6 +53,7 @@ __host__ __device__ inline SmemLayout make_layout(const RsScenario& sc) {
   m.off_hdr = o; o = align16(o + (size_t)kHdrInts * 4);
   m.off_misc = o; o = align16(o + 64 * 4);
   m.off_obs = o; o = align16(o + (size_t)(m.SL > 0 ? m.SL : 1) * 5 * 4);
+  m.off_mbar = o; o = align16(o + 16);
   m.total = o;
   return m;
 }
@@ -469,7 +470,7 @@ __device__ __forceinline__ void dev_set_phase(const RsScenario& sc, Tile& T, int
 
 template <int BLOCK>
 __device__ __forceinline__ void run_instance(const DevSim& D, const RunArgs& A, const SmemLayout& m,
-                                             unsigned char* smem, const int env) {
+                                             unsigned char* smem, const int env, uint32_t& tma_parity) {
   const RsScenario& sc = D.sc;
   const int tid = threadIdx.x % BLOCK;
   uint32_t* cur = (uint32_t*)(smem + m.off_bufA);
@@ -507,10 +508,23 @@ __device__ __forceinline__ void run_instance(const DevSim& D, const RunArgs& A, 
   {
     const uint32_t* g = D.veh + (size_t)env * kVehWords * m.vcap;
     const int n4 = (n0 + 3) >> 2;
-    for (int w = 0; w < kVehWords; ++w) {
-      const uint4* src = (const uint4*)(g + (size_t)w * m.vcap);
-      uint4* dst = (uint4*)(cur + (size_t)w * m.vcap);
-      for (int i = tid; i < n4; i += BLOCK) dst[i] = __ldcs(src + i);
+    if (D.use_tma) {        // TMA: ten 1-D bulk copies (one per word array) tracked by the slot's mbarrier
+      if (n4 > 0) {
+        uint64_t* bar = (uint64_t*)(smem + m.off_mbar);
+        if (tid == 0) {
+          mbar_expect_tx(bar, (uint32_t)(kVehWords * n4 * 16));
+          for (int w = 0; w < kVehWords; ++w)
+            tma_load_1d(cur + (size_t)w * m.vcap, g + (size_t)w * m.vcap, (uint32_t)(n4 * 16), bar);
+        }
+        mbar_wait(bar, tma_parity);
+        tma_parity ^= 1u;
+      }
+    } else {
+      for (int w = 0; w < kVehWords; ++w) {
+        const uint4* src = (const uint4*)(g + (size_t)w * m.vcap);
+        uint4* dst = (uint4*)(cur + (size_t)w * m.vcap);
+        for (int i = tid; i < n4; i += BLOCK) dst[i] = __ldcs(src + i);
+      }
     }
   }
   T.tick = hdr[H_TICK];
@@ -557,10 +571,20 @@ __device__ __forceinline__ void run_instance(const DevSim& D, const RunArgs& A, 
     const int n1 = hdr[H_NVEH];
     uint32_t* g = D.veh + (size_t)env * kVehWords * m.vcap;
     const int n4 = (n1 + 3) >> 2;
-    for (int w = 0; w < kVehWords; ++w) {
-      uint4* dst = (uint4*)(g + (size_t)w * m.vcap);
-      const uint4* src = (const uint4*)(cur + (size_t)w * m.vcap);
-      for (int i = tid; i < n4; i += BLOCK) __stcs(dst + i, src[i]);
+    if (D.use_tma) {        // shared -> global bulk stores; the tile may be reused once they have been READ
+      fence_proxy_async_smem();
+      __syncthreads();
+      if (tid == 0 && n4 > 0) {
+        for (int w = 0; w < kVehWords; ++w)
+          tma_store_1d(g + (size_t)w * m.vcap, cur + (size_t)w * m.vcap, (uint32_t)(n4 * 16));
+        tma_store_commit_and_wait_read();
+      }
+    } else {
+      for (int w = 0; w < kVehWords; ++w) {
+        uint4* dst = (uint4*)(g + (size_t)w * m.vcap);
+        const uint4* src = (const uint4*)(cur + (size_t)w * m.vcap);
+        for (int i = tid; i < n4; i += BLOCK) __stcs(dst + i, src[i]);
+      }
     }
   }
   if (tid < kHdrInts) D.hdr[(size_t)env * kHdrInts + tid] = hdr[tid];
@@ -585,6 +609,11 @@ __global__ void __launch_bounds__(TPI * G, MINB) k_run(const __grid_constant__ D
   const SmemLayout m = make_layout(D.sc);
   unsigned char* my = smem + (size_t)(threadIdx.x / TPI) * m.total;
   __shared__ int s_env;
+  uint32_t tma_parity = 0;
+  if (D.use_tma) {
+    if (threadIdx.x % TPI == 0) mbar_init((uint64_t*)(my + m.off_mbar), 1);
+    __syncthreads();
+  }
 #pragma unroll 1
   for (;;) {
     if (D.persistent) {
@@ -594,7 +623,7 @@ __global__ void __launch_bounds__(TPI * G, MINB) k_run(const __grid_constant__ D
     const int env0 = D.persistent ? s_env : (int)blockIdx.x * G;
     if (env0 >= D.n_env) break;
     // a slot past the end of the batch repeats the last instance (same inputs -> identical stores)
-    run_instance<TPI>(D, A, m, my, min(env0 + (int)(threadIdx.x / TPI), D.n_env - 1));
+    run_instance<TPI>(D, A, m, my, min(env0 + (int)(threadIdx.x / TPI), D.n_env - 1), tma_parity);
     if (!D.persistent) break;
     __syncthreads();
   }
@@ -868,6 +897,8 @@ extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, ui
   s->minb = (er ? atoi(er) != 0 : false) ? 1024 / (s->block * s->group) : 1;   // default: registers uncapped
   const char* ep = getenv("RESCO_B200_PERSIST");
   s->d.persistent = ep ? atoi(ep) : 1;
+  const char* et = getenv("RESCO_B200_TMA");
+  s->d.use_tma = et ? atoi(et) : 1;
   s->n_sm = prop.multiProcessorCount;
   TRY(dev_alloc(s, s->d.work_counter, 1));
   const char* ec = getenv("RESCO_B200_CARVEOUT");
