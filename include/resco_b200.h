@@ -126,6 +126,7 @@ typedef struct RsScenario {
   float speed_dev_override;          /* <0: use vType speedDev */
   int32_t vcap;                      /* max concurrently active vehicles per instance */
   int32_t lane_change;               /* 0 disables the lane-change decision */
+  int32_t record_trips;              /* keep a per-trip arrival record (tripinfo output); trip-table demand only */
 } RsScenario;
 
 /* Borrowed device pointers, valid until the next mutating call.  [N,...] row-major. */
@@ -200,6 +201,10 @@ int rs_dump_vehicles(RsSim* sim, int32_t env, int32_t* n_out, int32_t* lane, flo
                      float* accel, float* wait, float* rwait, float* tloss, int32_t* vid, int32_t* vtype,
                      int32_t* route, int32_t* cursor, float* sf, int32_t* depart);
 int rs_get_phases(RsSim* sim, int32_t env, int32_t* h_tls_phase /* [n_tls] */);
+/* `--tripinfo-output` (multi_signal.py:127-129): per-trip arrival records of one instance, indexed by trip
+ * (order of trip_depart/trip_route).  arrival[i] < 0: not arrived.  Needs RsScenario.record_trips. */
+int rs_get_trip_records(RsSim* sim, int32_t env, int32_t* h_arrival_tick, int32_t* h_depart_tick,
+                        float* h_time_loss, int32_t* h_depart_delay);
 int64_t rs_kernel_launches(RsSim* sim);
 /* device time (ms) of the last rs_env_step's kernels, CUDA events on the launching stream */
 int rs_last_step_ms(RsSim* sim, float* ms);

@@ -70,6 +70,7 @@ typedef struct {
   int32_t *sig_queue_len, *sig_max_queue;
   RsStats st;
   uint64_t env_id;
+  int32_t *trip_arrival, *trip_depart_tick, *trip_ddelay; float* trip_tloss;   /* [n_trips] when record_trips */
 } Inst;
 
 typedef struct OrcSim {
@@ -432,6 +433,10 @@ static int cmp_mover(const Inst* in, int a, int b) {
 }
 
 static void record_arrival(Inst* in, const Veh* x) {
+  if (in->trip_arrival) {
+    in->trip_arrival[x->vid] = in->tick; in->trip_depart_tick[x->vid] = x->depart;
+    in->trip_tloss[x->vid] = x->tloss; in->trip_ddelay[x->vid] = x->ddelay;
+  }
   in->st.n_arrived += 1;
   in->st.sum_delay_arrived += x->tloss + (float)x->ddelay;
   in->st.sum_duration_arrived += (float)(in->tick - x->depart);
@@ -775,6 +780,10 @@ OrcSim* orc_create(const RsScenario* sc, int32_t n_env, uint64_t seed) {
     in->rew_wait = (float*)own(s, 4 * (size_t)S); in->rew_wait_norm = (float*)own(s, 4 * (size_t)S);
     in->rew_pressure = (float*)own(s, 4 * (size_t)S);
     in->sig_queue_len = (int32_t*)own(s, 4 * (size_t)S); in->sig_max_queue = (int32_t*)own(s, 4 * (size_t)S);
+    if (sc->record_trips && !sc->synthetic) {
+      in->trip_arrival = (int32_t*)own(s, 4 * (size_t)sc->n_trips); in->trip_depart_tick = (int32_t*)own(s, 4 * (size_t)sc->n_trips);
+      in->trip_ddelay = (int32_t*)own(s, 4 * (size_t)sc->n_trips); in->trip_tloss = (float*)own(s, 4 * (size_t)sc->n_trips);
+    }
   }
   return s;
 }
@@ -797,6 +806,7 @@ void orc_reset(OrcSim* s, uint64_t seed, int64_t first_env_id) {
     memset(in->next_phase, 0, 4 * (size_t)sc->n_signals);
     memset(&in->st, 0, sizeof in->st);
     for (int t = 0; t < sc->n_tls; ++t) { in->tls_phase[t] = sc->tls_init_phase[t]; in->tls_end[t] = sc->tls_init_left[t]; }
+    if (in->trip_arrival) for (int i = 0; i < sc->n_trips; ++i) in->trip_arrival[i] = -1;
   }
 }
 
@@ -885,6 +895,15 @@ int orc_dump_vehicles(OrcSim* s, int32_t env, int32_t* lane, float* pos, float* 
       sf[i] = x->sf; depart[i] = x->depart;
     }
   return in->n_veh;
+}
+
+int orc_get_trip_records(OrcSim* s, int32_t env, int32_t* arrival, int32_t* depart, float* tloss, int32_t* ddelay) {
+  const Inst* in = &s->inst[env];
+  if (!in->trip_arrival) return -1;
+  size_t n = (size_t)s->sc.n_trips;
+  memcpy(arrival, in->trip_arrival, 4 * n); memcpy(depart, in->trip_depart_tick, 4 * n);
+  memcpy(tloss, in->trip_tloss, 4 * n); memcpy(ddelay, in->trip_ddelay, 4 * n);
+  return 0;
 }
 
 void orc_get_phases(OrcSim* s, int32_t env, int32_t* tls_phase) {

@@ -45,6 +45,8 @@ def lib():
         _LIB.orc_dump_vehicles.restype = C.c_int
         _LIB.orc_dump_vehicles.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 13
         _LIB.orc_get_phases.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        _LIB.orc_get_trip_records.restype = C.c_int
+        _LIB.orc_get_trip_records.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 4
         for f in ("orc_brake_gap", "orc_max_safe_stop_speed", "orc_free_speed"):
             getattr(_LIB, f).restype = C.c_float
             getattr(_LIB, f).argtypes = [C.c_float] * 3
@@ -128,6 +130,16 @@ class OracleSim:
         arrs = {n: np.zeros(self.vcap, dt) for n, dt in VEH_FIELDS}
         n = lib().orc_dump_vehicles(self._h, env, *[arrs[k].ctypes.data for k, _ in VEH_FIELDS])
         return {k: v[:n] for k, v in arrs.items()}
+
+    def trip_records(self, env: int = 0):
+        n = self.m.struct.n_trips
+        out = dict(arrival=np.zeros(n, np.int32), depart=np.zeros(n, np.int32), time_loss=np.zeros(n, np.float32),
+                   depart_delay=np.zeros(n, np.int32))
+        rc = lib().orc_get_trip_records(self._h, env, out["arrival"].ctypes.data, out["depart"].ctypes.data,
+                                        out["time_loss"].ctypes.data, out["depart_delay"].ctypes.data)
+        if rc != 0:
+            raise RuntimeError("trip records were not enabled (marshal(record_trips=True))")
+        return out
 
     def phases(self, env: int = 0):
         p = np.zeros(self.m.struct.n_tls, np.int32)

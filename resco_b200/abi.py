@@ -48,7 +48,7 @@ _PTRS: List[Tuple[str, object]] = [
 _PARAMS = [("synthetic", C.c_int32), ("synthetic_vtype", C.c_int32), ("step_length", C.c_int32),
            ("yellow_length", C.c_int32), ("end_tick", C.c_int32), ("max_distance", C.c_float),
            ("sigma_override", C.c_float), ("speed_dev_override", C.c_float), ("vcap", C.c_int32),
-           ("lane_change", C.c_int32)]
+           ("lane_change", C.c_int32), ("record_trips", C.c_int32)]
 
 
 class RsScenario(C.Structure):
@@ -118,7 +118,7 @@ def _ptr(arr: np.ndarray, ctype):
 
 def marshal(sc: Scenario, *, step_length: int = 10, yellow_length: int = 3, max_distance: float = 200.0,
             end_time: Optional[float] = None, controlled: bool = True, sigma: float = -1.0,
-            speed_dev: float = -1.0, vcap: int = 0, lane_change: bool = True,
+            speed_dev: float = -1.0, vcap: int = 0, lane_change: bool = True, record_trips: bool = False,
             synthetic: Optional[Dict[str, np.ndarray]] = None) -> Marshalled:
     """Build the C struct.  ``controlled=False`` keeps every tlLogic on its original program
     (the reference's FIXED rows: SUMO default programs, no Signal objects)."""
@@ -273,6 +273,7 @@ def marshal(sc: Scenario, *, step_length: int = 10, yellow_length: int = 3, max_
         vcap = default_vcap(sc)
     st.vcap = int(vcap)
     st.lane_change = 1 if lane_change else 0
+    st.record_trips = 1 if (record_trips and synthetic is None) else 0
     info = dict(programs_installed=programs_installed, yellow_dicts=yellow_dicts, signal_ids=sig_ids,
                 tls_ids=tls_ids, green_states=green_states_of, vcap=int(vcap), sizes=sizes)
     return Marshalled(st, keep, info)

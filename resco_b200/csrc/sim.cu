@@ -66,7 +66,7 @@ struct OriginCand { int32_t route, vt, vid, ok_dd, unsafe; };   // ok_dd: -1 not
 // ------------------------------------------------------------------------------------------------
 template <int BLOCK>
 __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, unsigned char* smem, Tile& T, uint32_t*& cur,
-                          uint32_t*& oth) {
+                          uint32_t*& oth, const int env) {
   const RsScenario& sc = D.sc;
   const int tid = threadIdx.x % BLOCK;   // BLOCK = threads per instance (a CTA may hold several instances)
   const int L = m.L;
@@ -146,6 +146,9 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
     T.meta[i] = mt;
     if (curl < 0) {
       newlane[i] = (uint16_t)kArrived;
+      if (D.trip_rec)   // tripinfo record (multi_signal.py:127-129)
+        D.trip_rec[(size_t)env * sc.n_trips + T.vid[i]] =
+            make_int4(T.tick, (int)(T.ed[i] >> 16), __float_as_int(T.tloss[i]), (int)(T.dl[i] & 0xFFFFu));
       atomicAdd(&cnt2[l], -1);
       int s = atomicAdd(&misc[M_NARR], 1);
       arr[s] = (uint16_t)i;
@@ -562,7 +565,7 @@ __device__ __forceinline__ void run_instance(const DevSim& D, const RunArgs& A, 
       __syncthreads();
     }
     if (k == n_ticks) break;
-    tick_body<BLOCK>(D, m, smem, T, cur, oth);
+    tick_body<BLOCK>(D, m, smem, T, cur, oth, env);
   }
   if (A.do_observe) observe_body<BLOCK>(D, m, smem, T, env);
 
@@ -643,6 +646,8 @@ __global__ void k_reset(DevSim D) {
     D.origin_cur[(size_t)env * sc.n_origins + i] = 0;
     D.origin_backlog[(size_t)env * sc.n_origins + i] = 0;
   }
+  if (D.trip_rec)
+    for (int i = threadIdx.x; i < sc.n_trips; i += blockDim.x) D.trip_rec[(size_t)env * sc.n_trips + i] = make_int4(-1, 0, 0, 0);
 }
 
 __global__ void k_set_phase(DevSim D, const int32_t* phase, const uint8_t* mask) {
@@ -876,6 +881,8 @@ extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, ui
   TRY(dev_alloc(s, s->d.sig_queue_len, N * S)); TRY(dev_alloc(s, s->d.sig_max_queue, N * S));
   TRY(dev_alloc(s, s->d_actions, N * (S ? S : 1)));
   TRY(dev_alloc(s, s->d_stats, N));
+  s->d.trip_rec = nullptr;
+  if (sc->record_trips && !sc->synthetic && sc->n_trips > 0) TRY(dev_alloc(s, s->d.trip_rec, N * (size_t)sc->n_trips));
   CK(cudaMallocHost((void**)&s->h_act_pinned, sizeof(int32_t) * N * (S ? S : 1)));
   CK(cudaMallocHost((void**)&s->h_obs_pinned, sizeof(float) * N * (S ? S : 1) * 13));
   CK(cudaMallocHost((void**)&s->h_rew_pinned, sizeof(float) * N * (S ? S : 1)));
@@ -1065,6 +1072,24 @@ extern "C" int rs_get_phases(RsSim* s, int32_t env, int32_t* h_tls_phase) {
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(h_tls_phase, s->d.tls_phase + (size_t)env * s->d.sc.n_tls, sizeof(int32_t) * s->d.sc.n_tls,
                 cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int rs_get_trip_records(RsSim* s, int32_t env, int32_t* h_arrival_tick, int32_t* h_depart_tick,
+                                   float* h_time_loss, int32_t* h_depart_delay) {
+  if (!s || env < 0 || env >= s->d.n_env) return fail(RS_ERR_INVALID, "rs_get_trip_records: bad arguments");
+  if (!s->d.trip_rec) return fail(RS_ERR_INVALID, "rs_get_trip_records: RsScenario.record_trips was not set");
+  CK(cudaSetDevice(s->device));
+  CK(cudaDeviceSynchronize());
+  const size_t n = (size_t)s->d.sc.n_trips;
+  std::vector<int4> buf(n);
+  CK(cudaMemcpy(buf.data(), s->d.trip_rec + (size_t)env * n, sizeof(int4) * n, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < n; ++i) {
+    if (h_arrival_tick) h_arrival_tick[i] = buf[i].x;
+    if (h_depart_tick) h_depart_tick[i] = buf[i].y;
+    if (h_time_loss) memcpy(&h_time_loss[i], &buf[i].z, 4);
+    if (h_depart_delay) h_depart_delay[i] = buf[i].w;
+  }
   return 0;
 }
 

@@ -69,7 +69,8 @@ class MultiSignal(_EnvBase):
                  step_length=10, yellow_length=4, step_ratio=1, max_distance=200, lights=(), log_dir='/',
                  libsumo=False, warmup=0, gymma=False, *, n_env: int = 1, device: int = 0,
                  seed: Optional[int] = None, backend: Optional[Callable[[Marshalled], object]] = None,
-                 scenario: Optional[Scenario] = None, vcap: int = 0, sigma: float = -1.0, speed_dev: float = -1.0):
+                 scenario: Optional[Scenario] = None, vcap: int = 0, sigma: float = -1.0, speed_dev: float = -1.0,
+                 tripinfo: Optional[bool] = None):
         if warmup != 0:
             raise NotImplementedError("warmup ticks before program installation are not supported (all shipped maps use 0)")
         if step_ratio != 1:
@@ -91,9 +92,11 @@ class MultiSignal(_EnvBase):
         self.seed = seed
         self.scenario = scenario if scenario is not None else load_scenario(map_name)
         sc = self.scenario
+        # tripinfo_<run>.xml like `--tripinfo-output` (multi_signal.py:127-129): on by default for n_env == 1
+        self.tripinfo = (self.n_env == 1 and log_dir is not None) if tripinfo is None else bool(tripinfo)
         self.marshalled = marshal(sc, step_length=step_length, yellow_length=yellow_length,
                                   max_distance=float(max_distance), end_time=float(end_time), vcap=vcap,
-                                  sigma=sigma, speed_dev=speed_dev)
+                                  sigma=sigma, speed_dev=speed_dev, record_trips=self.tripinfo)
         m = self.marshalled
         self.sim = (backend or _default_backend(self.n_env, device))(m)
         self._begin = float(sc.meta["begin"])
@@ -238,9 +241,19 @@ class MultiSignal(_EnvBase):
             self.sim.tick(1)
             self._tick += 1
 
+    def save_tripinfo(self):
+        """tripinfo_<run>.xml of instance 0 (readable by utils/readXML.py)."""
+        from .metrics import write_tripinfo
+        os.makedirs(self._log_path(), exist_ok=True)
+        path = os.path.join(self._log_path(), 'tripinfo_' + str(self.run) + '.xml')
+        write_tripinfo(path, self.scenario, self.sim.trip_records(0), self.sim.vehicles(0), self._tick)
+        return path
+
     def reset(self):
         if self.run != 0:
             self.save_metrics()
+            if self.tripinfo:
+                self.save_tripinfo()
         self.metrics = []
         self.run += 1
         self._episode_seed = (self.run if self.seed is None else int(self.seed) + self.run - 1)
@@ -316,5 +329,7 @@ class MultiSignal(_EnvBase):
     def close(self):
         if self.run != 0:
             self.save_metrics()
+            if self.tripinfo:
+                self.save_tripinfo()
         if hasattr(self.sim, "close"):
             self.sim.close()

@@ -39,7 +39,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
 EXPORTS = ["rs_last_error", "rs_abi_version", "rs_create", "rs_destroy", "rs_reset", "rs_set_phase", "rs_tick",
            "rs_observe", "rs_env_step", "rs_env_step_host", "rs_policy_maxpressure", "rs_get_obs", "rs_get_stats",
-           "rs_dump_vehicles", "rs_get_phases", "rs_kernel_launches", "rs_last_step_ms"]
+           "rs_dump_vehicles", "rs_get_phases", "rs_get_trip_records", "rs_kernel_launches", "rs_last_step_ms"]
 
 
 def load_library():
@@ -67,6 +67,7 @@ def load_library():
     lib.rs_get_stats.argtypes = [C.c_void_p, C.c_void_p]
     lib.rs_dump_vehicles.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32)] + [C.c_void_p] * 13
     lib.rs_get_phases.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    lib.rs_get_trip_records.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 4
     lib.rs_kernel_launches.restype = C.c_int64
     lib.rs_kernel_launches.argtypes = [C.c_void_p]
     lib.rs_last_step_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
@@ -231,6 +232,14 @@ class VecSim:
         p = np.zeros(self.m.struct.n_tls, np.int32)
         _check(self.lib, self.lib.rs_get_phases(self._h, env, p.ctypes.data))
         return p
+
+    def trip_records(self, env: int = 0) -> Dict[str, np.ndarray]:
+        n = self.m.struct.n_trips
+        out = dict(arrival=np.zeros(n, np.int32), depart=np.zeros(n, np.int32), time_loss=np.zeros(n, np.float32),
+                   depart_delay=np.zeros(n, np.int32))
+        _check(self.lib, self.lib.rs_get_trip_records(self._h, env, out["arrival"].ctypes.data, out["depart"].ctypes.data,
+                                                      out["time_loss"].ctypes.data, out["depart_delay"].ctypes.data))
+        return out
 
     def kernel_launches(self) -> int:
         return int(self.lib.rs_kernel_launches(self._h))
