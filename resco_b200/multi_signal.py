@@ -165,6 +165,14 @@ class MultiSignal(_EnvBase):
         self.lane_sig_t
         return self._lane_slot_t
 
+    def mdp_config(self, key):
+        """mdp_configs[key][map] with the 'supervisors' reverse map (main.py:48-70)."""
+        cfg = dict(self.scenario.meta.get('mdp', {}).get(key) or {})
+        if not cfg:
+            raise KeyError(f"no {key} configuration for map '{self.map_name}'")
+        cfg['supervisors'] = {w: mgr for mgr, workers in cfg['management'].items() for w in workers}
+        return cfg
+
     def _make_signals(self):
         for i, ts in enumerate(self.signal_ids):
             self.signals[ts] = Signal(self, ts, i)

@@ -100,6 +100,68 @@ def wave(signals):
     return out
 
 
+def _mdp(signals, key):
+    """mdp_configs[key] of the map (config/mdp_config.py), with the worker->manager reverse map that
+    main.py:62-70 precomputes under 'supervisors'."""
+    env = next(iter(signals.values()))._env
+    return env.mdp_config(key)
+
+
+def _region_fringes(signals, cfg):
+    """Inbound lanes through which traffic enters a manager's region (states.py:168-180)."""
+    supervisors = cfg['supervisors']
+    fringes = {mgr: [] for mgr in cfg['management']}
+    for sid, sig in signals.items():
+        for key, neighbor in sig.downstream.items():
+            if neighbor is None or supervisors[neighbor] != supervisors[sid]:
+                inbounds = sig.inbounds_fr_direction.get(key)
+                if inbounds is not None:
+                    fringes[supervisors[sid]] += inbounds
+    return fringes
+
+
+def _fma2c(signals, key, full):
+    cfg = _mdp(signals, key)
+    supervisors, neighbors_of = cfg['supervisors'], cfg['management_neighbors']
+    fringes = _region_fringes(signals, cfg)
+    lane_wave = {lane: sig.full_observation[lane]['queue'] + sig.full_observation[lane]['approach']
+                 for sig in signals.values() for lane in sig.lanes}
+    manager_obs = {mgr: np.clip(np.asarray([lane_wave[l] for l in lanes]) / cfg['norm_wave'], 0, cfg['clip_wave'])
+                   for mgr, lanes in fringes.items()}
+    managers = {mgr: np.concatenate([manager_obs[mgr]] + [cfg['alpha'] * manager_obs[nb] for nb in neighbors_of[mgr]])
+                for mgr in manager_obs}
+    signal_wave = dict()
+    for sid, sig in signals.items():
+        waves = []
+        for lane in sig.lanes:
+            waves.append(lane_wave[lane])
+            if full:
+                waves.append(sig.full_observation[lane]['total_wait'] / 28)
+                waves.append(_speed_sum_norm(sig, lane))
+        signal_wave[sid] = np.clip(np.asarray(waves) / cfg['norm_wave'], 0, cfg['clip_wave'])
+    out = dict()
+    for sid, sig in signals.items():
+        waves = [signal_wave[sid]]
+        for neighbor in sig.downstream.values():
+            if neighbor is not None and supervisors[neighbor] == supervisors[sid]:
+                waves.append(cfg['alpha'] * signal_wave[neighbor])
+        waits = np.clip(np.asarray([sig.full_observation[l]['max_wait'] for l in sig.lanes]) / cfg['norm_wait'],
+                        0, cfg['clip_wait'])
+        out[sid] = np.concatenate([np.concatenate(waves), waits])
+    out.update(managers)
+    return out
+
+
+def fma2c(signals):
+    """states.py:162-229 -- worker obs (own + same-region neighbour waves, max waits) + manager obs."""
+    return _fma2c(signals, 'FMA2C', full=False)
+
+
+def fma2c_full(signals):
+    """states.py:232-305."""
+    return _fma2c(signals, 'FMA2CFull', full=True)
+
+
 # ---- batched device views (N instances) ----------------------------------------------------------
 def _b_mplight(env):
     return env.sim.obs_view()["mplight"]

@@ -31,7 +31,8 @@ def _run_case(path, backend):
     order = meta["ts_order"]
     assert env.ts_order == order
     assert {ts: list(env.obs_shape[ts]) for ts in order} == meta["obs_shapes"]
-    for ts in order:          # create_yellows + installed program (traffic_signal.py:7-24,93-100)
+    real = [ts for ts in order if ts in env.signals]      # manager pseudo-agents (FMA2C) are not signals
+    for ts in real:           # create_yellows + installed program (traffic_signal.py:7-24,93-100)
         assert env.signals[ts].yellow_dict == meta["yellow_dicts"][ts]
         assert [s for _, s in env.signals[ts].phases] == [s for _, s in meta["programs"][ts]]
         assert env.signals[ts].lanes == meta["lanes"][ts]
@@ -40,16 +41,16 @@ def _run_case(path, backend):
     got = np.concatenate([np.asarray(obs[ts], np.float64).ravel() for ts in order])
     np.testing.assert_allclose(got, z["reset_obs"], rtol=1e-9, atol=1e-12)
     for step in range(z["act"].shape[0]):
-        act = {ts: int(z["act"][step, i]) for i, ts in enumerate(order)}
+        act = {ts: int(z["act"][step, i]) for i, ts in enumerate(order) if ts in env.signals}
         obs, rew, done, info = env.step(act)
         got = np.concatenate([np.asarray(obs[ts], np.float64).ravel() for ts in order])
         np.testing.assert_allclose(got, z["obs"][step], rtol=1e-6, atol=1e-9, err_msg=f"obs step {step}")
         np.testing.assert_allclose([float(rew[ts]) for ts in order], z["rew"][step], rtol=1e-6, atol=1e-9,
                                    err_msg=f"reward step {step}")
-        assert [env.signals[ts].phase for ts in order] == z["phase"][step].tolist(), f"phase step {step}"
+        assert [env.signals[ts].phase if ts in env.signals else -1 for ts in order] == z["phase"][step].tolist(), f"phase step {step}"
         mt = env.metrics[-1]
-        assert [mt["queue_lengths"][ts] for ts in order] == z["queue_lengths"][step].tolist()
-        assert [mt["max_queues"][ts] for ts in order] == z["max_queues"][step].tolist()
+        assert [mt["queue_lengths"].get(ts, -1) for ts in order] == z["queue_lengths"][step].tolist()
+        assert [mt["max_queues"].get(ts, -1) for ts in order] == z["max_queues"][step].tolist()
         assert mt["step"] == z["step_time"][step]
     env.close()
 

@@ -21,6 +21,7 @@ OUT = os.path.join(os.path.dirname(__file__), '..', 'resco_b200', 'data')
 def main(maps):
     signal_configs = runpy.run_path(os.path.join(REF, 'config', 'signal_config.py'))['signal_configs']
     map_configs = runpy.run_path(os.path.join(REF, 'config', 'map_config.py'))['map_configs']
+    mdp_configs = runpy.run_path(os.path.join(REF, 'config', 'mdp_config.py'))['mdp_configs']
     os.makedirs(OUT, exist_ok=True)
     for m in maps:
         mc = map_configs[m]
@@ -38,6 +39,8 @@ def main(maps):
                 demand = read_routes_xml(z.read(m + '_1.rou.xml').decode(), is_text=True)
             begin = float(mc['start_time'])
         sc = compile_scenario(net, demand, m, mc, signal_configs[m], begin)
+        # hyper-parameters + manager/worker regions of the FMA2C states/rewards (config/mdp_config.py)
+        sc.meta['mdp'] = {k: mdp_configs[k][m] for k in ('FMA2C', 'FMA2CFull') if m in mdp_configs.get(k, {})}
         path = os.path.join(OUT, m + '.npz')
         sc.save(path)
         a = sc.arrays

@@ -100,6 +100,12 @@ def ref_env(map_name, state_name, reward_name, max_distance, yellow_length=None)
     mc = importlib.import_module('resco_benchmark.config.map_config').map_configs[map_name]
     yl = mc['yellow_length'] if yellow_length is None else yellow_length
     CFG.update(step_length=mc['step_length'], yellow_length=yl, max_distance=float(max_distance), next_seed=0)
+    if state_name.startswith('fma2c'):          # main.py:48-70: per-map mdp config + 'supervisors' reverse map
+        mdp = importlib.import_module('resco_benchmark.config.mdp_config').mdp_configs
+        key = 'FMA2CFull' if state_name == 'fma2c_full' else 'FMA2C'
+        cfgm = dict(mdp[key][map_name]) if map_name in mdp[key] else dict(mdp[key])
+        cfgm['supervisors'] = {w: mgr for mgr, ws in cfgm['management'].items() for w in ws}
+        mdp[key] = cfgm
     net = os.path.join(REF, mc['net'])
     route = os.path.join(REF, mc['route']) if mc['route'] is not None else None
     if route is not None:
@@ -117,7 +123,7 @@ def record(map_name, state_name, reward_name, max_distance, n_steps, policy, see
     rng = np.random.default_rng(seed)
     obs = env.reset()
     order = list(env.ts_order)
-    n_act = {ts: len(env.phases[ts]) for ts in order}
+    n_act = {ts: len(env.phases[ts]) for ts in order if ts in env.phases}
     agent = None
     if policy in ('MAXPRESSURE', 'MAXWAVE'):
         agent_mod = importlib.import_module('resco_benchmark.agents.' + ('maxpressure' if policy == 'MAXPRESSURE' else 'maxwave'))
@@ -132,26 +138,27 @@ def record(map_name, state_name, reward_name, max_distance, n_steps, policy, see
             act = agent.act(obs)
         else:
             act = {}
-            for ts in order:        # random, with some holding so that both branches of prep_phase are taken
+            for ts in [t for t in order if t in n_act]:   # random, with some holding (both prep_phase branches)
                 if hold[ts] <= 0:
                     cur[ts] = int(rng.integers(n_act[ts]))
                     hold[ts] = int(rng.integers(1, 4))
                 hold[ts] -= 1
                 act[ts] = cur[ts]
         obs, rew, done, info = env.step(act)
-        rec['act'].append([int(act[ts]) for ts in order])
+        rec['act'].append([int(act.get(ts, -1)) for ts in order])
         rec['obs'].append(np.concatenate([np.asarray(obs[ts], np.float64).ravel() for ts in order]))
         rec['rew'].append([float(rew[ts]) for ts in order])
-        rec['phase'].append([int(env.signals[ts].phase) for ts in order])
+        rec['phase'].append([int(env.signals[ts].phase) if ts in env.signals else -1 for ts in order])
         mt = env.metrics[-1]
-        rec['queue_lengths'].append([mt['queue_lengths'][ts] for ts in order])
-        rec['max_queues'].append([mt['max_queues'][ts] for ts in order])
+        rec['queue_lengths'].append([mt['queue_lengths'].get(ts, -1) for ts in order])
+        rec['max_queues'].append([mt['max_queues'].get(ts, -1) for ts in order])
         rec['step_time'].append(mt['step'])
-    yellows = {ts: env.signals[ts].yellow_dict for ts in order}
-    programs = {ts: [[p.duration, p.state] for p in env.signals[ts].phases] for ts in order}
+    real = [ts for ts in order if ts in env.signals]
+    yellows = {ts: env.signals[ts].yellow_dict for ts in real}
+    programs = {ts: [[p.duration, p.state] for p in env.signals[ts].phases] for ts in real}
     meta = dict(map=map_name, state=state_name, reward=reward_name, max_distance=max_distance, policy=policy,
                 ts_order=order, obs_shapes={ts: list(env.obs_shape[ts]) for ts in order}, yellow_dicts=yellows,
-                programs=programs, lanes={ts: env.signals[ts].lanes for ts in order},
+                programs=programs, lanes={ts: env.signals[ts].lanes for ts in real},
                 step_length=mc['step_length'], yellow_length=CFG['yellow_length'], episode_seed=1,
                 n_actions=n_act)
     env.close()
@@ -178,6 +185,8 @@ def main():
     record('cologne3', 'drq', 'wait', 200, 60, 'random', seed=5)
     record('ingolstadt21', 'mplight', 'pressure', 200, 60, 'random', seed=6)
     record('ingolstadt21', 'drq_norm', 'wait_norm', 200, 40, 'random', seed=7)
+    record('cologne8', 'fma2c', 'fma2c', 200, 80, 'random', seed=8)
+    record('ingolstadt7', 'fma2c_full', 'fma2c_full', 200, 50, 'random', seed=9)
 
 
 if __name__ == '__main__':
