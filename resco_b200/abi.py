@@ -309,6 +309,8 @@ def smem_bytes(vcap: int, n_lanes: int, n_tls: int, n_signals: int, n_origins: i
     o = al(o + 64 * 4)
     o = al(o + max(n_sig_lanes, 1) * 20)
     o = al(o + 16)
+    o = al(o + (2 * vcap + max(n_origins, 1)) * 2)
+    o = al(o + max(n_origins, 1) * 2)
     return o
 
 

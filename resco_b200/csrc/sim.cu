@@ -20,7 +20,7 @@ struct SmemLayout {
   size_t off_bufA, off_bufB, off_vn, off_newlane, off_newidx, off_mnext, off_arr;
   size_t off_lane_start, off_start2, off_cnt2, off_mhead;
   size_t off_tls_phase, off_tls_end, off_tls_state, off_next_phase, off_origin_cur, off_origin_backlog, off_origin_cand;
-  size_t off_vt, off_hdr, off_misc, off_obs, off_mbar;
+  size_t off_vt, off_hdr, off_misc, off_obs, off_mbar, off_dirty, off_oklist;
   size_t total;
 };
 
@@ -54,19 +54,23 @@ __host__ __device__ inline SmemLayout make_layout(const RsScenario& sc) {
   m.off_misc = o; o = align16(o + 64 * 4);
   m.off_obs = o; o = align16(o + (size_t)(m.SL > 0 ? m.SL : 1) * 5 * 4);
   m.off_mbar = o; o = align16(o + 16);
+  m.off_dirty = o; o = align16(o + ((size_t)2 * m.vcap + (size_t)(m.O > 0 ? m.O : 1)) * 2);   // lanes touched this tick
+  m.off_oklist = o; o = align16(o + (size_t)(m.O > 0 ? m.O : 1) * 2);                          // origins with a candidate
   m.total = o;
   return m;
 }
 
 // misc slots
-enum { M_NARR = 0, M_NOK, M_NAFTER, M_WARP = 16 /* 32 ints of warp totals */ };
+enum { M_NARR = 0, M_NOK, M_NAFTER, M_NDIRTY, M_NOKC, M_WARP = 16 /* 32 ints of warp totals */ };
+
+constexpr int kDirty = 0x40000000;   // flag bit in cnt2[l]: the lane gained or lost a vehicle this tick
 
 struct OriginCand { int32_t route, vt, vid, ok_dd, unsafe; };   // ok_dd: -1 not ok, else depart delay
 
 // ------------------------------------------------------------------------------------------------
 template <int BLOCK>
 __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, unsigned char* smem, Tile& T, uint32_t*& cur,
-                          uint32_t*& oth, const int env) {
+                          uint32_t*& oth, uint16_t*& start2, const int env) {
   const RsScenario& sc = D.sc;
   const int tid = threadIdx.x % BLOCK;   // BLOCK = threads per instance (a CTA may hold several instances)
   const int L = m.L;
@@ -75,8 +79,9 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
   uint16_t* newidx = (uint16_t*)(smem + m.off_newidx);
   uint16_t* mnext = (uint16_t*)(smem + m.off_mnext);
   uint16_t* arr = (uint16_t*)(smem + m.off_arr);
-  uint16_t* start2 = (uint16_t*)(smem + m.off_start2);
-  int32_t* cnt2 = (int32_t*)(smem + m.off_cnt2);
+  int32_t* cnt2 = (int32_t*)(smem + m.off_cnt2);     // per-lane vehicle count, kept current across ticks
+  uint16_t* dirty = (uint16_t*)(smem + m.off_dirty);
+  uint16_t* oklist = (uint16_t*)(smem + m.off_oklist);
   int32_t* mhead = (int32_t*)(smem + m.off_mhead);
   int32_t* hdr = (int32_t*)(smem + m.off_hdr);
   int32_t* misc = (int32_t*)(smem + m.off_misc);
@@ -97,9 +102,14 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
     }
     T.tls_state[t] = __ldg(sc.phase_state_off + p0 + T.tls_phase[t]);
   }
-  for (int l = tid; l < L; l += BLOCK) { cnt2[l] = lane_count(T, l); mhead[l] = -1; }
-  if (tid == 0) { misc[M_NARR] = 0; misc[M_NOK] = 0; }
+  if (tid == 0) { misc[M_NARR] = 0; misc[M_NOK] = 0; misc[M_NDIRTY] = 0; misc[M_NOKC] = 0; }
   __syncthreads();
+
+  // a lane that gains or loses a vehicle is put on the dirty list once (flag bit in its counter)
+  auto mark_dirty = [&](int l) {
+    int old = atomicOr(&cnt2[l], kDirty);
+    if (!(old & kDirty)) { int s = atomicAdd(&misc[M_NDIRTY], 1); dirty[s] = (uint16_t)l; }
+  };
 
   // ---- S1: plan (reads only start-of-tick state) ----
   for (int i = tid; i < n; i += BLOCK) {
@@ -150,6 +160,7 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
         D.trip_rec[(size_t)env * sc.n_trips + T.vid[i]] =
             make_int4(T.tick, (int)(T.ed[i] >> 16), __float_as_int(T.tloss[i]), (int)(T.dl[i] & 0xFFFFu));
       atomicAdd(&cnt2[l], -1);
+      mark_dirty(l);
       int s = atomicAdd(&misc[M_NARR], 1);
       arr[s] = (uint16_t)i;
     } else {
@@ -157,6 +168,7 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
       if (curl != l) {
         atomicAdd(&cnt2[l], -1);
         atomicAdd(&cnt2[curl], 1);
+        mark_dirty(l); mark_dirty(curl);
         int old = atomicExch(&mhead[curl], i);
         mnext[i] = (uint16_t)(old < 0 ? 0xFFFF : old);
       }
@@ -226,7 +238,7 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
           if (T.pos[tailv] - VTT(T, tvt, VT_LEN) - len - mingap < 0.0f) ok = false;
         }
       }
-      if (ok) c.ok_dd = dd;
+      if (ok) { c.ok_dd = dd; int s = atomicAdd(&misc[M_NOKC], 1); oklist[s] = (uint16_t)o; }
     }
     cand[o] = c;
   }
@@ -234,10 +246,11 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
 
   // ---- S3a': upstream safety of the candidates, one thread per (origin, watch lane) pair:
   //      nobody who is about to drive onto an origin lane may be forced into hard braking ----
-  for (int w = tid; w < sc.n_watch; w += BLOCK) {
-    int o = __ldg(sc.origin_watch_owner + w);
-    if (cand[o].ok_dd < 0) continue;
-    int lane = __ldg(sc.origin_lane + o);
+  const int nokc = misc[M_NOKC];
+  for (int j = 0; j < nokc; ++j) {
+   const int o = oklist[j];
+   const int lane = __ldg(sc.origin_lane + o);
+   for (int w = __ldg(sc.origin_watch_off + o) + tid; w < __ldg(sc.origin_watch_off + o + 1); w += BLOCK) {
     int pl = __ldg(sc.origin_watch_lane + w);
     // post-move head of pl: first stayer of the old segment vs. the front-most mover into pl
     int a = T.lane_start[pl], b = T.lane_start[pl + 1];
@@ -264,10 +277,12 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
     int hvt = v_vtype(T, h);
     float gap = (__ldg(sc.lane_len + pl) - T.pos[h]) + __ldg(sc.origin_watch_dist + w) - VTT(T, hvt, VT_GAP);
     if (gap < brake_gap(T.speed[h], VTT(T, hvt, VT_DECEL), VTT(T, hvt, VT_TAU))) cand[o].unsafe = 1;
+   }
   }
   __syncthreads();
-  for (int o = tid; o < m.O; o += BLOCK) {
-    if (cand[o].ok_dd >= 0) { if (cand[o].unsafe) cand[o].ok_dd = -1; else atomicAdd(&misc[M_NOK], 1); }
+  for (int j = tid; j < nokc; j += BLOCK) {
+    const int o = oklist[j];
+    if (cand[o].unsafe) cand[o].ok_dd = -1; else atomicAdd(&misc[M_NOK], 1);
   }
   __syncthreads();
 
@@ -275,33 +290,36 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
   {
     const int n_after = misc[M_NAFTER], n_ok = misc[M_NOK];
     const bool all = n_after + n_ok <= m.vcap;
-    for (int o = tid; o < m.O; o += BLOCK) {
+    for (int j = tid; j < nokc; j += BLOCK) {
+      const int o = oklist[j];
       if (cand[o].ok_dd < 0) continue;
       bool acc = all;
       if (!all) {
         int before = 0;
-        for (int q = 0; q < o; ++q) before += cand[q].ok_dd >= 0;
+        for (int q = 0; q < o; ++q) before += cand[q].ok_dd >= 0 || cand[q].ok_dd == -2;
         acc = n_after + before < m.vcap;
       }
       if (acc) {
-        atomicAdd(&cnt2[__ldg(sc.origin_lane + o)], 1);
+        const int lane = __ldg(sc.origin_lane + o);
+        atomicAdd(&cnt2[lane], 1);
+        mark_dirty(lane);
         atomicAdd(&hdr[H_NINS], 1);
-      } else cand[o].ok_dd = -2;   // refused by capacity
+        origin_cur[o] += 1;
+        if (sc.synthetic) origin_backlog[o] -= 1;
+      } else cand[o].ok_dd = -2;   // refused by capacity (still counts as "ok before" for later origins)
     }
   }
   __syncthreads();
-  for (int o = tid; o < m.O; o += BLOCK) {
-    if (cand[o].ok_dd >= 0) { origin_cur[o] += 1; if (sc.synthetic) origin_backlog[o] -= 1; }
-  }
 
   // ---- S4: new lane offsets ----
-  block_prefix<BLOCK>(cnt2, start2, L, misc + M_WARP);
+  block_prefix<BLOCK>(cnt2, start2, L, misc + M_WARP);   // counts are read without the dirty flag bit
 
   // ---- S5: per-lane merge: stayers keep their order, movers merge in by position ----
-  for (int l = tid; l < L; l += BLOCK) {
+  const int ndirty = misc[M_NDIRTY];
+  for (int dj = tid; dj < ndirty; dj += BLOCK) {
+    const int l = dirty[dj];
     int a = T.lane_start[l], b = T.lane_start[l + 1];
     int head = mhead[l];
-    if (a == b && head < 0) continue;
     int w = start2[l];
     // next mover in (pos desc, idx asc) order after (ppos, pidx)
     float ppos = 3.0e38f; int pidx = -1;
@@ -331,12 +349,14 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
     for (int i = tid; i < n; i += BLOCK) {
       uint32_t nl = newlane[i];
       if (nl == kArrived) continue;
-      int d = newidx[i];
+      // untouched lane: the segment only shifts; touched lanes were merged above
+      int d = (cnt2[nl] & kDirty) ? (int)newidx[i] : (int)start2[nl] + (i - (int)T.lane_start[nl]);
       U.pos[d] = T.pos[i]; U.speed[d] = T.speed[i]; U.sf[d] = T.sf[i]; U.tloss[d] = T.tloss[i];
       U.vid[d] = T.vid[i]; U.wr[d] = T.wr[i]; U.rc[d] = T.rc[i]; U.meta[d] = T.meta[i]; U.ed[d] = T.ed[i];
       U.dl[d] = (T.dl[i] & 0xFFFFu) | (nl << 16);
     }
-    for (int o = tid; o < m.O; o += BLOCK) {
+    for (int j = tid; j < nokc; j += BLOCK) {
+      const int o = oklist[j];
       OriginCand c = cand[o];
       if (c.ok_dd < 0) continue;
       int lane = __ldg(sc.origin_lane + o);
@@ -355,8 +375,9 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
   {
     uint32_t* tmp = cur; cur = oth; oth = tmp;
     tile_bind(T, cur, m.vcap);
-    for (int l = tid; l <= L; l += BLOCK) T.lane_start[l] = start2[l];
-    const int n2 = start2[L];
+    for (int dj = tid; dj < ndirty; dj += BLOCK) { const int l = dirty[dj]; cnt2[l] &= ~kDirty; mhead[l] = -1; }
+    { uint16_t* t2 = T.lane_start; T.lane_start = start2; start2 = t2; }    // lane offsets ping-pong
+    const int n2 = T.lane_start[L];
     if (tid == 0) {
       hdr[H_NVEH] = n2;
       hdr[H_ACTIVE] += n2;
@@ -540,6 +561,15 @@ __device__ __forceinline__ void run_instance(const DevSim& D, const RunArgs& A, 
   }
   __syncthreads();
 
+  // per-lane counters stay current from tick to tick; only the lanes a tick touches are revisited
+  uint16_t* start2 = (uint16_t*)(smem + m.off_start2);
+  {
+    int32_t* cnt2 = (int32_t*)(smem + m.off_cnt2);
+    int32_t* mhead = (int32_t*)(smem + m.off_mhead);
+    for (int l = tid; l < m.L; l += BLOCK) { cnt2[l] = lane_count(T, l); mhead[l] = -1; }
+  }
+  __syncthreads();
+
   // ---- MultiSignal.step schedule (multi_signal.py:164-197) ----
   if (A.do_prep) {
     for (int sg = tid; sg < m.S; sg += BLOCK) {   // Signal.prep_phase (traffic_signal.py:176-184)
@@ -565,7 +595,7 @@ __device__ __forceinline__ void run_instance(const DevSim& D, const RunArgs& A, 
       __syncthreads();
     }
     if (k == n_ticks) break;
-    tick_body<BLOCK>(D, m, smem, T, cur, oth, env);
+    tick_body<BLOCK>(D, m, smem, T, cur, oth, start2, env);
   }
   if (A.do_observe) observe_body<BLOCK>(D, m, smem, T, env);
 

@@ -517,7 +517,7 @@ __device__ void block_prefix(const int32_t* cnt, uint16_t* start, int n, int32_t
   const int per = (n + BLOCK - 1) / BLOCK;
   const int a = min(tid * per, n), b = min(a + per, n);
   int s = 0;
-  for (int i = a; i < b; ++i) s += cnt[i];
+  for (int i = a; i < b; ++i) s += cnt[i] & 0x3FFFFFFF;
   int inc = s;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -529,7 +529,7 @@ __device__ void block_prefix(const int32_t* cnt, uint16_t* start, int n, int32_t
   int base = 0;
   for (int w = 0; w < wid; ++w) base += warp_tot[w];
   int run = base + inc - s;
-  for (int i = a; i < b; ++i) { start[i] = (uint16_t)run; run += cnt[i]; }
+  for (int i = a; i < b; ++i) { start[i] = (uint16_t)run; run += cnt[i] & 0x3FFFFFFF; }
   if (tid == BLOCK - 1) start[n] = (uint16_t)run;
   __syncthreads();
 }
