@@ -193,6 +193,9 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
     hdr[H_NARR] += na;
   }
   for (int o = tid; o < m.O; o += BLOCK) {
+    // trip-table demand: origin_backlog[o] holds the departure time of the origin's next trip (float bits),
+    // so an origin with nothing due costs one shared-memory compare
+    if (!sc.synthetic && !(__int_as_float(origin_backlog[o]) <= (float)T.tick)) { cand[o].ok_dd = -1; continue; }
     int lane = __ldg(sc.origin_lane + o);
     OriginCand c; c.ok_dd = -1; c.route = 0; c.vt = 0; c.vid = 0; c.unsafe = 0;
     bool have = false;
@@ -306,6 +309,10 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
         atomicAdd(&hdr[H_NINS], 1);
         origin_cur[o] += 1;
         if (sc.synthetic) origin_backlog[o] -= 1;
+        else {
+          const int ci = __ldg(sc.origin_off + o) + origin_cur[o];
+          origin_backlog[o] = __float_as_int(ci < __ldg(sc.origin_off + o + 1) ? __ldg(sc.trip_depart + ci) : 3.0e38f);
+        }
       } else cand[o].ok_dd = -2;   // refused by capacity (still counts as "ok before" for later origins)
     }
   }
@@ -523,8 +530,13 @@ __device__ __forceinline__ void run_instance(const DevSim& D, const RunArgs& A, 
   }
   for (int i = tid; i < m.S; i += BLOCK) next_phase[i] = D.next_phase[(size_t)env * m.S + i];
   for (int i = tid; i < m.O; i += BLOCK) {
-    origin_cur[i] = D.origin_cur[(size_t)env * m.O + i];
-    origin_backlog[i] = D.origin_backlog[(size_t)env * m.O + i];
+    const int oc = D.origin_cur[(size_t)env * m.O + i];
+    origin_cur[i] = oc;
+    if (sc.synthetic) origin_backlog[i] = D.origin_backlog[(size_t)env * m.O + i];
+    else {   // departure time of the next trip of this origin (see S3a)
+      const int ci = __ldg(sc.origin_off + i) + oc;
+      origin_backlog[i] = __float_as_int(ci < __ldg(sc.origin_off + i + 1) ? __ldg(sc.trip_depart + ci) : 3.0e38f);
+    }
   }
   for (int i = tid; i < m.n_vt * 8; i += BLOCK) vt[i] = __ldg(sc.vtype + i);
   __syncthreads();
@@ -628,7 +640,7 @@ __device__ __forceinline__ void run_instance(const DevSim& D, const RunArgs& A, 
   for (int i = tid; i < m.S; i += BLOCK) D.next_phase[(size_t)env * m.S + i] = next_phase[i];
   for (int i = tid; i < m.O; i += BLOCK) {
     D.origin_cur[(size_t)env * m.O + i] = origin_cur[i];
-    D.origin_backlog[(size_t)env * m.O + i] = origin_backlog[i];
+    if (sc.synthetic) D.origin_backlog[(size_t)env * m.O + i] = origin_backlog[i];
   }
 }
 
