@@ -125,3 +125,52 @@ def test_synthetic_grid_parity():
     for k in sg.dtype.names:
         assert np.array_equal(sg[k], so[k]), (k, sg[k], so[k])
     assert (sg["n_backlog"] > 0).any()          # demand above capacity: the backlog path is exercised
+
+
+def test_full_size_batch_properties():
+    """BASELINE configs[1] at FULL size (cologne8 / MaxPressure / 4096 lock-step instances): size-independent
+    properties + oracle spot checks.  (a) vehicle conservation and zero ordering anomalies in every instance,
+    (b) instances are independent and keyed by their global id: instance i of the 4096-batch is bit-identical to
+    the oracle run alone with first_env_id = i under the same actions, (c) a second run reproduces the first."""
+    from pyoracle import OracleSim
+    from resco_b200.sim import VecSim
+    sc, m = util.marshal_map("cologne8", vcap=128)
+    N, steps = 4096, 40
+    pairs, va, sig = sc.meta["phase_pairs"], sc.meta["valid_acts"], m.info["signal_ids"]
+    picks = [0, 1, 777, 2048, 4095]
+
+    def run():
+        g = VecSim(m, N, seed=11)
+        g.reset(11, 0)
+        g.observe()
+        acts = []
+        for _ in range(steps):
+            a = g.policy_maxpressure(pairs, va, sig)
+            acts.append(a[picks].cpu().numpy().copy())
+            g.env_step(a)
+        return g, acts
+
+    g, acts = run()
+    st = g.stats()
+    assert (st["anomalies"] == 0).all()
+    assert (st["n_inserted"] == st["n_arrived"] + st["n_active"]).all()
+    assert (st["tick"] == steps * m.struct.step_length).all()
+    assert len(np.unique(st["sum_delay_running"])) > N // 2          # instances really differ (driver randomness)
+    og = g.obs()
+    for j, i in enumerate(picks):
+        o = OracleSim(m, 1, seed=11)
+        o.reset(11, i)
+        o.observe()
+        for s in range(steps):
+            o.env_step(acts[s][j:j + 1])
+        vo, vg = o.vehicles(0), g.vehicles(i)
+        for k in util.VEH_EXACT:
+            assert np.array_equal(vo[k], vg[k]), (i, k)
+        oo = o.obs()
+        for k in util.OBS_EXACT:
+            assert np.array_equal(oo[k][0], og[k][i]), (i, k)
+    g2, _ = run()
+    st2 = g2.stats()
+    for k in st.dtype.names:
+        assert np.array_equal(st[k], st2[k]), k
+    assert np.array_equal(g2.obs()["mplight"], og["mplight"])
