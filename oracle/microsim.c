@@ -365,6 +365,10 @@ static void plan_vehicle(const OrcSim* s, Inst* in, int i, int lane, int rank) {
     int mask = sc->route_mask[ro + x->cursor];
     int bestm = (mask >> 8) & 0xFF;
     int dir = strategic_dir(sc, x, lane), strategic = dir != 0;
+    /* urgent: the route cannot continue from this lane and the lane end is near (or the vehicle already
+     * stands): accept any gap the neighbours can still handle with emergency braking */
+    int urgent = strategic && !((mask >> sc->lane_index[lane]) & 1) &&
+                 (sc->lane_len[lane] - x->pos < 60.0f || x->wait > 3.0f);
     for (int pass = 0; pass < 2; ++pass) {
       /* pass 0: strategic direction (if any); pass 1 (no strategic need): speed gain, left then right */
       int d;
@@ -389,14 +393,16 @@ static void plan_vehicle(const OrcSim* s, Inst* in, int i, int lane, int rank) {
         if (gap < 0.0f) ok = 0;
         else {
           vfol = follow_speed(gap, ld->speed, VT(s, ld->vtype, VT_DECEL), decel, tau);
-          if (vfol < v - decel) ok = 0;
+          if (vfol < v - (urgent ? fmaxf(decel, EMERGENCY_DECEL) : decel)) ok = 0;
         }
       }
       if (ok && j < b) {
         const Veh* fo = &in->veh[j];
         float gap = x->pos - len - fo->pos - VT(s, fo->vtype, VT_GAP);
         if (gap < 0.0f) ok = 0;
-        else {
+        else if (urgent) {
+          if (gap < brake_gap(fo->speed, fmaxf(VT(s, fo->vtype, VT_DECEL), EMERGENCY_DECEL), 0.0f)) ok = 0;
+        } else {
           float vf = follow_speed(gap, v, decel, VT(s, fo->vtype, VT_DECEL), VT(s, fo->vtype, VT_TAU));
           if (vf < fo->speed + VT(s, fo->vtype, VT_ACCEL) - VT(s, fo->vtype, VT_DECEL)) ok = 0;
         }

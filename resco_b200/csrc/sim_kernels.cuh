@@ -413,6 +413,10 @@ RS_HEAVY void plan_vehicle(const RsScenario& sc, const Tile& t, int i, float& vn
     int bestm = (mask >> 8) & 0xFF;
     int dir = strategic_dir(sc, route, cursor, lane);
     bool strategic = dir != 0;
+    // urgent: the route cannot continue from this lane and the lane end is near (or the vehicle already
+    // stands): accept any gap the neighbours can still handle with emergency braking
+    const bool urgent = strategic && !((mask >> __ldg(sc.lane_index + lane)) & 1) &&
+                        (lane_len - x < 60.0f || v_wait(t, i) > 3);
     int vbit = __ldg(sc.vtype_bit + vt);
     for (int pass = 0; pass < 2; ++pass) {
       int d;
@@ -436,14 +440,16 @@ RS_HEAVY void plan_vehicle(const RsScenario& sc, const Tile& t, int i, float& vn
         if (gap < 0.0f) ok = false;
         else {
           vfol = follow_speed(gap, t.speed[ld], VTT(t, lvt, VT_DECEL), decel, tau);
-          if (vfol < v - decel) ok = false;
+          if (vfol < v - (urgent ? fmaxf(decel, kEmergencyDecel) : decel)) ok = false;
         }
       }
       if (ok && j < b) {
         int fvt = v_vtype(t, j);
         float gap = x - len - t.pos[j] - VTT(t, fvt, VT_GAP);
         if (gap < 0.0f) ok = false;
-        else {
+        else if (urgent) {
+          if (gap < brake_gap(t.speed[j], fmaxf(VTT(t, fvt, VT_DECEL), kEmergencyDecel), 0.0f)) ok = false;
+        } else {
           float vf = follow_speed(gap, v, decel, VTT(t, fvt, VT_DECEL), VTT(t, fvt, VT_TAU));
           if (vf < t.speed[j] + VTT(t, fvt, VT_ACCEL) - VTT(t, fvt, VT_DECEL)) ok = false;
         }
