@@ -140,7 +140,7 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
     else {
       int guard = 0;
       while (p > __ldg(sc.lane_len + curl) && guard++ < 64) {
-        int k = guard == 1 ? v_nextlink(sc, T, i, l) : choose_link(sc, curl, route, cc);
+        int k = guard == 1 ? v_nextlink(sc, T, i, l) : next_link(sc, curl, route, cc);
         if (k == -1) { curl = -1; break; }
         if (k == -2) { p = __ldg(sc.lane_len + curl); break; }
         p -= __ldg(sc.lane_len + curl);
@@ -152,7 +152,7 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
     T.pos[i] = p;
     T.rc[i] = (T.rc[i] & 0xFFFFu) | ((uint32_t)cc << 16);
     uint32_t mt = (T.meta[i] & 0xFFFF00FFu) | ((uint32_t)lcc << 8);
-    if (curl >= 0 && curl != l) mt = (mt & 0x00FFFFFFu) | (encode_nextlink(sc, curl, choose_link(sc, curl, route, cc)) << 24);
+    if (curl >= 0 && curl != l) mt = (mt & 0x00FFFFFFu) | (encode_nextlink(sc, curl, next_link(sc, curl, route, cc)) << 24);
     T.meta[i] = mt;
     if (curl < 0) {
       newlane[i] = (uint16_t)kArrived;
@@ -268,7 +268,7 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
     int cur = pl, cc = v_cursor(T, h), hr = v_route(T, h);
     bool reaches = false;
     for (int hop = 0; hop < 4; ++hop) {
-      int k = hop == 0 ? v_nextlink(sc, T, h, pl) : choose_link(sc, cur, hr, cc);
+      int k = hop == 0 ? v_nextlink(sc, T, h, pl) : next_link(sc, cur, hr, cc);
       if (k < 0) break;
       int via = __ldg(sc.link_via + k);
       int nxt = via >= 0 ? via : __ldg(sc.link_to + k);

@@ -209,6 +209,15 @@ __device__ __noinline__ int choose_link(const RsScenario& sc, int lane, int rout
   return best;
 }
 
+// choose_link with the internal-lane case (exactly one way on) resolved inline, without the call
+__device__ __forceinline__ int next_link(const RsScenario& sc, int lane, int route, int cursor) {
+  if (__ldg(sc.lane_internal + lane)) {
+    int k0 = __ldg(sc.lane_link_off + lane);
+    return k0 < __ldg(sc.lane_link_off + lane + 1) ? k0 : -2;
+  }
+  return choose_link(sc, lane, route, cursor);
+}
+
 __device__ __forceinline__ int state_now(const RsScenario& sc, const Tile& t, int k) {
   int tl = __ldg(sc.link_tls + k);
   if (tl < 0) return __ldg(sc.link_state + k);
@@ -317,7 +326,7 @@ RS_HEAVY bool must_stop(const RsScenario& sc, const Tile& t, int i, int k, float
     if (free_room > 0.0f) space += free_room;
     if (space >= need) return false;
     if (lane_count(t, cur) > 0) break;
-    int k2 = choose_link(sc, cur, route, cc2);
+    int k2 = next_link(sc, cur, route, cc2);
     if (k2 < 0) return false;
     if (!__ldg(sc.lane_internal + cur)) {
       int st2 = state_now(sc, t, k2);
@@ -369,7 +378,7 @@ RS_HEAVY void plan_vehicle(const RsScenario& sc, const Tile& t, int i, float& vn
     int cur = lane, cc = cursor;
     float la = brake_gap(vacc, decel, 0.0f) + 2.0f * vacc + 5.0f;
     for (int hop = 0; hop < kMaxHops; ++hop) {
-      int k = hop == 0 ? v_nextlink(sc, t, i, lane) : choose_link(sc, cur, route, cc);
+      int k = hop == 0 ? v_nextlink(sc, t, i, lane) : next_link(sc, cur, route, cc);
       if (k == -1) break;
       if (k == -2) {
         vsafe = fminf(vsafe, max_safe_stop_speed(seen, decel, tau));
