@@ -174,3 +174,58 @@ def test_full_size_batch_properties():
     for k in st.dtype.names:
         assert np.array_equal(st[k], st2[k]), k
     assert np.array_equal(g2.obs()["mplight"], og["mplight"])
+
+
+@pytest.mark.parametrize("case", ["tile_full", "drain_to_empty", "arterial_5s_steps", "deterministic_driver",
+                                  "short_detector", "odd_batch"])
+def test_edge_cases(case):
+    """Edge cases of the domain: saturated tile (insertion refused in origin order), empty network before
+    the first and after the last departure, 5 s env steps with 2 s yellows and a second vType, the
+    deterministic-driver configuration (sigma = speedDev = 0), a 1 m detector range (STOCHASTIC agent
+    config), and a batch size that is not a multiple of the CTA's instance group."""
+    from pyoracle import OracleSim
+    from resco_b200.sim import VecSim
+    kw, name, n_env, steps, policy = {}, "cologne8", 2, 40, "cyclic"
+    if case == "tile_full":
+        kw, steps = dict(vcap=24), 60                      # far below the ~55 vehicles the map wants
+    elif case == "drain_to_empty":
+        name, n_env, steps = "cologne1", 2, 0
+    elif case == "arterial_5s_steps":
+        name, steps = "arterial4x4", 80
+    elif case == "deterministic_driver":
+        kw = dict(sigma=0.0, speed_dev=0.0)
+    elif case == "short_detector":
+        kw = dict(max_distance=1.0)
+    elif case == "odd_batch":
+        n_env, steps = 13, 15
+    sc, m = util.marshal_map(name, **kw)
+    g = VecSim(m, n_env, seed=3); o = OracleSim(m, n_env, seed=3)
+    g.reset(3, 5); o.reset(3, 5)
+    g.observe(); o.observe()
+    og = g.obs()
+    assert (og["lane_queue"] == 0).all() and (og["mplight"][:, :, 1:] == 0).all()     # empty network at reset
+    util.assert_same_obs(og, o.obs(), "reset")
+    if case == "drain_to_empty":
+        # jump to the end of the demand and let the network run empty
+        for _ in range(8):
+            g.tick(500); o.tick(500)
+        sg, so = g.stats(), o.stats()
+        assert (sg["n_active"] == 0).all() and (sg["n_backlog"] == 0).all()
+        for k in sg.dtype.names:
+            assert np.array_equal(sg[k], so[k]), k
+        g.observe(); o.observe()
+        util.assert_same_obs(g.obs(), o.obs(), "empty again")
+        return
+    for step in range(steps):
+        act = util.cyclic_actions(m, n_env, step)
+        g.env_step(act); o.env_step(act)
+        util.assert_same_obs(g.obs(), o.obs(), f"{case} step {step}")
+    for e in range(n_env):
+        util.assert_same_state(g, o, e, f"{case} env {e}")
+    sg, so = g.stats(), o.stats()
+    for k in sg.dtype.names:
+        assert np.array_equal(sg[k], so[k]), (case, k)
+    if case == "tile_full":
+        assert (sg["n_active"] <= 24).all() and (sg["n_backlog"] > 0).any()
+    if case == "deterministic_driver":
+        assert (g.vehicles(0)["sf"] == 1.0).all()
