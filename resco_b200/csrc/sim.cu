@@ -1016,19 +1016,28 @@ extern "C" int rs_env_step(RsSim* s, const int32_t* d_actions, void* stream) {
   return 0;
 }
 
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
 extern "C" int rs_env_step_host(RsSim* s, const int32_t* h_actions, float* h_obs, float* h_reward, int32_t reward_kind) {
   if (!s || !h_actions) return fail(RS_ERR_INVALID, "rs_env_step_host: bad arguments");
   const size_t NS = (size_t)s->d.n_env * s->d.sc.n_signals;
-  memcpy(s->h_act_pinned, h_actions, sizeof(int32_t) * NS);
-  CK(cudaMemcpyAsync(s->d_actions, s->h_act_pinned, sizeof(int32_t) * NS, cudaMemcpyHostToDevice, 0));
+  // page-locked caller buffers are used directly; pageable ones go through the sim's pinned staging buffers
+  const bool pa = is_pinned(h_actions), po = !h_obs || is_pinned(h_obs), pr = !h_reward || is_pinned(h_reward);
+  const int32_t* src = h_actions;
+  if (!pa) { memcpy(s->h_act_pinned, h_actions, sizeof(int32_t) * NS); src = s->h_act_pinned; }
+  CK(cudaMemcpyAsync(s->d_actions, src, sizeof(int32_t) * NS, cudaMemcpyHostToDevice, 0));
   int r = rs_env_step(s, s->d_actions, nullptr);
   if (r) return r;
   const float* rew = reward_kind == 0 ? s->d.rew_wait : (reward_kind == 1 ? s->d.rew_wait_norm : s->d.rew_pressure);
-  if (h_obs) CK(cudaMemcpyAsync(s->h_obs_pinned, s->d.mplight, sizeof(float) * NS * 13, cudaMemcpyDeviceToHost, 0));
-  if (h_reward) CK(cudaMemcpyAsync(s->h_rew_pinned, rew, sizeof(float) * NS, cudaMemcpyDeviceToHost, 0));
+  if (h_obs) CK(cudaMemcpyAsync(po ? h_obs : s->h_obs_pinned, s->d.mplight, sizeof(float) * NS * 13, cudaMemcpyDeviceToHost, 0));
+  if (h_reward) CK(cudaMemcpyAsync(pr ? h_reward : s->h_rew_pinned, rew, sizeof(float) * NS, cudaMemcpyDeviceToHost, 0));
   CK(cudaStreamSynchronize(0));
-  if (h_obs) memcpy(h_obs, s->h_obs_pinned, sizeof(float) * NS * 13);
-  if (h_reward) memcpy(h_reward, s->h_rew_pinned, sizeof(float) * NS);
+  if (h_obs && !po) memcpy(h_obs, s->h_obs_pinned, sizeof(float) * NS * 13);
+  if (h_reward && !pr) memcpy(h_reward, s->h_rew_pinned, sizeof(float) * NS);
   return 0;
 }
 

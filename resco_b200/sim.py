@@ -163,13 +163,20 @@ class VecSim:
         _check(self.lib, self.lib.rs_env_step(self._h, actions.data_ptr(), self._stream()))
 
     def env_step_host(self, actions: np.ndarray, reward_kind: int = 0):
-        """End-to-end call with HOST buffers (H2D actions, D2H mplight obs + reward)."""
-        a = np.ascontiguousarray(actions, np.int32)
-        obs = np.empty((self.n_env, self.S, 13), np.float32)
-        rew = np.empty((self.n_env, self.S), np.float32)
-        _check(self.lib, self.lib.rs_env_step_host(self._h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data,
+        """End-to-end call with HOST buffers (H2D actions, D2H mplight obs + reward).  The returned arrays
+        are page-locked buffers owned by this object and are overwritten by the next call."""
+        if getattr(self, "_host_bufs", None) is None:
+            t = self._torch
+            self._host_bufs = (t.empty((self.n_env, self.S), dtype=t.int32).pin_memory(),
+                               t.empty((self.n_env, self.S, 13), dtype=t.float32).pin_memory(),
+                               t.empty((self.n_env, self.S), dtype=t.float32).pin_memory())
+            self._host_np = tuple(b.numpy() for b in self._host_bufs)
+        act_t, obs_t, rew_t = self._host_bufs
+        act_np, obs_np, rew_np = self._host_np
+        np.copyto(act_np, np.asarray(actions).reshape(self.n_env, self.S), casting="unsafe")
+        _check(self.lib, self.lib.rs_env_step_host(self._h, act_t.data_ptr(), obs_t.data_ptr(), rew_t.data_ptr(),
                                                    reward_kind))
-        return obs, rew
+        return obs_np, rew_np
 
     def policy_maxpressure(self, pairs, valid_acts, signal_ids, use_wave: bool = False):
         """Batched MAXPRESSURE / MAXWAVE on the device -> [N, S] int32 CUDA tensor of actions."""
