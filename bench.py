@@ -300,6 +300,7 @@ def run_ours(args):
                        "l2": "flushed between timed steps (256 MiB memset, untimed)",
                        "timing": "per-step CUDA events on the launching stream, summed; max over ranks",
                        "allgather_obs": bool(gather_buf is not None),
+                       "avg_delay_parity_vs_sumo": "not measurable here: SUMO/libsumo is installed neither in the build container nor on the GPU box; statistical anchors against utils/avg_timeLoss.py are in DESIGN.md section 7",
                        "preroll_env_steps": args.preroll,
                        "episode_window": "timed steps start after an untimed pre-roll of the episode (loaded network); the episode restarts (reset + pre-roll, untimed) when its 360 steps are used up"},
             "sim_ticks_per_s": value * m.struct.step_length,
