@@ -466,6 +466,36 @@ def green_phase_indices(program: List[List[object]]) -> List[int]:
     return [i for i, (_d, st) in enumerate(program) if 'y' not in st and 'g' in st.lower()]
 
 
+def generate_signal_config(sig_id: str, controlled_links: List[List[List[str]]]) -> Dict[str, object]:
+    """Fallback topology for a signal without a ``signal_configs`` entry, restating
+    ``Signal.generate_config`` (traffic_signal.py:106-164): every third controlled link opens one of the
+    12 movements in the fixed order S-W, S-S, S-E, W-N, ... ; the inbound lane of that link is the
+    movement's lane set; the downstream signal of a direction is the first ``letters+digits`` token of
+    the through-lane's id unless it names a fringe (top/right/left/bottom).  ``lanes`` keeps the order in
+    which inbound lanes first appear in the link list.  (Like the reference, no outbound lane sets are
+    derived: states that subtract downstream queues need a real ``signal_configs`` entry.)"""
+    import re
+    order = ['S-W', 'S-S', 'S-E', 'W-N', 'W-W', 'W-S', 'N-E', 'N-N', 'N-W', 'E-S', 'E-E', 'E-N']
+    lane_sets: Dict[str, List[str]] = {mv: [] for mv in order}
+    lanes: List[str] = []
+    for i, slot in enumerate(controlled_links):
+        if not slot:
+            continue
+        inbound = slot[0][0]
+        if inbound not in lanes:
+            lanes.append(inbound)
+        if i % 3 == 0 and i // 3 < len(order):
+            lane_sets[order[i // 3]].append(inbound)
+    downstream: Dict[str, Optional[str]] = {'N': None, 'E': None, 'S': None, 'W': None}
+    for through, direction in (('S-S', 'N'), ('N-N', 'S'), ('W-W', 'E'), ('E-E', 'W')):
+        if not lane_sets[through]:
+            continue
+        tokens = re.findall('[a-zA-Z]+[0-9]+', lane_sets[through][0])
+        if tokens and not any(f in tokens[0] for f in ('top', 'right', 'left', 'bottom')):
+            downstream[direction] = tokens[0]
+    return dict(lane_sets=lane_sets, downstream=downstream, lanes=lanes)
+
+
 def compile_signals(meta: Dict[str, object], idx: Dict[str, object], signal_config: Dict[str, object],
                     lights: Sequence[str]) -> Tuple[Dict[str, np.ndarray], Dict[str, object]]:
     """Per-signal lane topology, in the iteration order of ``traffic_signal.py:46-87``."""
@@ -488,16 +518,22 @@ def compile_signals(meta: Dict[str, object], idx: Dict[str, object], signal_conf
     sig_meta = {}
     # pass 1: lane lists
     lanes_of: Dict[str, List[str]] = {}
+    cfg_of: Dict[str, Dict[str, object]] = {}
     for s in sig_ids:
-        cfg = signal_config[s]
-        lanes: List[str] = []
-        for direction in cfg['lane_sets']:
-            for lane in cfg['lane_sets'][direction]:
-                if lane not in lanes:
-                    lanes.append(lane)
+        if s in signal_config:
+            cfg = signal_config[s]
+            lanes: List[str] = []
+            for direction in cfg['lane_sets']:
+                for lane in cfg['lane_sets'][direction]:
+                    if lane not in lanes:
+                        lanes.append(lane)
+        else:       # Signal.generate_config fallback (traffic_signal.py:88-89,106-164)
+            cfg = generate_signal_config(s, meta["controlled_links"][s])
+            lanes = list(cfg['lanes'])
+        cfg_of[s] = cfg
         lanes_of[s] = lanes
     for s in sig_ids:
-        cfg = signal_config[s]
+        cfg = cfg_of[s]
         lane_sets = cfg['lane_sets']
         downstream = cfg['downstream']
         lanes = lanes_of[s]
@@ -515,7 +551,9 @@ def compile_signals(meta: Dict[str, object], idx: Dict[str, object], signal_conf
             dwn = downstream[direction]
             if dwn is None:
                 continue
-            dwn_lane_sets = signal_config[dwn]['lane_sets']
+            if dwn not in cfg_of or 'lanes' in cfg:     # generated configs derive no outbound lane sets
+                continue
+            dwn_lane_sets = cfg_of[dwn]['lane_sets']
             for key in dwn_lane_sets:
                 if key.split('-')[0] == direction:
                     dwn_lane_set = dwn_lane_sets[key]

@@ -62,3 +62,23 @@ def test_marshal_programs():
         assert all('y' in st for _, st in prog[ng:])
         assert all(d == 3 for d, _ in prog[ng:])
     assert m.struct.n_signals == 8 and m.struct.n_sig_lanes == 33
+
+
+def test_generate_config_matches_reference():
+    """Signal.generate_config fallback (traffic_signal.py:106-164): golden produced by the reference class
+    itself on grid4x4 under a map name without a signal_configs entry (tools/make_golden_generate_config.py)."""
+    import json, os
+    from resco_b200.scenario.compiler import generate_signal_config
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "generate_config_grid4x4.json")))
+    sc = util.load("grid4x4")
+    assert set(gold) == set(sc.meta["tls_ids"])
+    for t, want in gold.items():
+        got = generate_signal_config(t, sc.meta["controlled_links"][t])
+        assert got["lanes"] == want["lanes"], t
+        assert got["lane_sets"] == want["lane_sets"], t
+        assert got["downstream"] == want["downstream"], t
+    # and on this regular grid the generated topology equals the hand-written signal_configs entry
+    for t in sc.meta["tls_ids"]:
+        got = generate_signal_config(t, sc.meta["controlled_links"][t])
+        assert got["lane_sets"] == sc.meta["signals"][t]["lane_sets"], t
+        assert got["downstream"] == sc.meta["signals"][t]["downstream"], t
