@@ -241,55 +241,43 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
           if (T.pos[tailv] - VTT(T, tvt, VT_LEN) - len - mingap < 0.0f) ok = false;
         }
       }
-      if (ok) { c.ok_dd = dd; int s = atomicAdd(&misc[M_NOKC], 1); oklist[s] = (uint16_t)o; }
+      // upstream safety: nobody who is about to drive onto this lane may be forced into hard braking
+      for (int w = __ldg(sc.origin_watch_off + o); ok && w < __ldg(sc.origin_watch_off + o + 1); ++w) {
+    int pl = __ldg(sc.origin_watch_lane + w);
+      // post-move head of pl: first stayer of the old segment vs. the front-most mover into pl
+      int a = T.lane_start[pl], b = T.lane_start[pl + 1];
+      int hs = -1;
+      for (int i = a; i < b; ++i) if (newlane[i] == pl) { hs = i; break; }
+      int hm = -1;
+      for (int q = mhead[pl]; q >= 0; q = (mnext[q] == 0xFFFF ? -1 : (int)mnext[q]))
+        if (hm < 0 || T.pos[q] > T.pos[hm] || (T.pos[q] == T.pos[hm] && q < hm)) hm = q;
+      int h = hs;
+      if (hm >= 0 && (hs < 0 || T.pos[hm] > T.pos[hs])) h = hm;
+      if (h < 0) continue;
+      int cur = pl, cc = v_cursor(T, h), hr = v_route(T, h);
+      bool reaches = false;
+      for (int hop = 0; hop < 4; ++hop) {
+        int k = hop == 0 ? v_nextlink(sc, T, h, pl) : next_link(sc, cur, hr, cc);
+        if (k < 0) break;
+        int via = __ldg(sc.link_via + k);
+        int nxt = via >= 0 ? via : __ldg(sc.link_to + k);
+        if (nxt == lane) { reaches = true; break; }
+        if (!__ldg(sc.lane_internal + nxt)) cc += 1;
+        cur = nxt;
+      }
+      if (!reaches) continue;
+      int hvt = v_vtype(T, h);
+      float gap = (__ldg(sc.lane_len + pl) - T.pos[h]) + __ldg(sc.origin_watch_dist + w) - VTT(T, hvt, VT_GAP);
+      if (gap < brake_gap(T.speed[h], VTT(T, hvt, VT_DECEL), VTT(T, hvt, VT_TAU))) ok = false;
+      }
+      if (ok) { c.ok_dd = dd; int s = atomicAdd(&misc[M_NOKC], 1); oklist[s] = (uint16_t)o; atomicAdd(&misc[M_NOK], 1); }
     }
     cand[o] = c;
   }
   __syncthreads();
 
-  // ---- S3a': upstream safety of the candidates, one thread per (origin, watch lane) pair:
-  //      nobody who is about to drive onto an origin lane may be forced into hard braking ----
-  const int nokc = misc[M_NOKC];
-  for (int j = 0; j < nokc; ++j) {
-   const int o = oklist[j];
-   const int lane = __ldg(sc.origin_lane + o);
-   for (int w = __ldg(sc.origin_watch_off + o) + tid; w < __ldg(sc.origin_watch_off + o + 1); w += BLOCK) {
-    int pl = __ldg(sc.origin_watch_lane + w);
-    // post-move head of pl: first stayer of the old segment vs. the front-most mover into pl
-    int a = T.lane_start[pl], b = T.lane_start[pl + 1];
-    int hs = -1;
-    for (int i = a; i < b; ++i) if (newlane[i] == pl) { hs = i; break; }
-    int hm = -1;
-    for (int q = mhead[pl]; q >= 0; q = (mnext[q] == 0xFFFF ? -1 : (int)mnext[q]))
-      if (hm < 0 || T.pos[q] > T.pos[hm] || (T.pos[q] == T.pos[hm] && q < hm)) hm = q;
-    int h = hs;
-    if (hm >= 0 && (hs < 0 || T.pos[hm] > T.pos[hs])) h = hm;
-    if (h < 0) continue;
-    int cur = pl, cc = v_cursor(T, h), hr = v_route(T, h);
-    bool reaches = false;
-    for (int hop = 0; hop < 4; ++hop) {
-      int k = hop == 0 ? v_nextlink(sc, T, h, pl) : next_link(sc, cur, hr, cc);
-      if (k < 0) break;
-      int via = __ldg(sc.link_via + k);
-      int nxt = via >= 0 ? via : __ldg(sc.link_to + k);
-      if (nxt == lane) { reaches = true; break; }
-      if (!__ldg(sc.lane_internal + nxt)) cc += 1;
-      cur = nxt;
-    }
-    if (!reaches) continue;
-    int hvt = v_vtype(T, h);
-    float gap = (__ldg(sc.lane_len + pl) - T.pos[h]) + __ldg(sc.origin_watch_dist + w) - VTT(T, hvt, VT_GAP);
-    if (gap < brake_gap(T.speed[h], VTT(T, hvt, VT_DECEL), VTT(T, hvt, VT_TAU))) cand[o].unsafe = 1;
-   }
-  }
-  __syncthreads();
-  for (int j = tid; j < nokc; j += BLOCK) {
-    const int o = oklist[j];
-    if (cand[o].unsafe) cand[o].ok_dd = -1; else atomicAdd(&misc[M_NOK], 1);
-  }
-  __syncthreads();
-
   // ---- S3b: capacity resolution (origin order) ----
+  const int nokc = misc[M_NOKC];
   {
     const int n_after = misc[M_NAFTER], n_ok = misc[M_NOK];
     const bool all = n_after + n_ok <= m.vcap;
