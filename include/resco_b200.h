@@ -187,6 +187,14 @@ int rs_env_step(RsSim* sim, const int32_t* d_actions, void* stream);
 /* Same through HOST buffers (the end-to-end call): copies actions H2D, steps, copies
  * obs/reward back; h_obs [N,S,13] mplight, h_reward [N,S] (kind: 0 wait, 1 wait_norm, 2 pressure). */
 int rs_env_step_host(RsSim* sim, const int32_t* h_actions, float* h_obs, float* h_reward, int32_t reward_kind);
+/* Asynchronous form of rs_env_step_host: enqueues actions H2D -> env step -> obs/reward D2H on `stream` and
+ * returns at once; rs_wait() blocks until that step's results are in h_obs / h_reward.  The three buffers must
+ * stay valid (and h_actions unchanged) until rs_wait returns.  Two sims that each hold half of a batch, driven
+ * alternately on two streams, let the host-side agent of one half overlap the device step of the other -- the
+ * vectorised-env form of the reference's act -> step loop (main.py:run_trial).  One pending step per sim. */
+int rs_env_step_host_async(RsSim* sim, const int32_t* h_actions, float* h_obs, float* h_reward, int32_t reward_kind,
+                           void* stream);
+int rs_wait(RsSim* sim);
 /* Batched MaxPressure / MaxWave action selection on the device (agents/maxwave.py:18-38 over
  * states.mplight[1:] / states.wave): writes [N,S] actions.  pairs [n_pairs,2]; order [S, n_pairs, 2] =
  * (pair index, action) in the reference's evaluation order (iteration order of valid_acts[signal]),

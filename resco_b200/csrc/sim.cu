@@ -767,8 +767,9 @@ struct RsSim {
   int resident_ctas;
   std::vector<void*> allocs;
   int64_t launches;
-  cudaEvent_t ev0, ev1;
+  cudaEvent_t ev0, ev1, ev_done;
   bool timed;
+  bool pending; float* pend_obs; float* pend_rew;   // rs_env_step_host_async -> rs_wait
   // host staging for rs_env_step_host
   int32_t* h_act_pinned; float* h_obs_pinned; float* h_rew_pinned;
   int32_t* d_actions;
@@ -862,6 +863,7 @@ extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, ui
   if (prop.major < 10) return fail(RS_ERR_NODEVICE, "rs_create: built for sm_100a (Blackwell) only");
   RsSim* s = new RsSim();
   s->device = device; s->launches = 0; s->timed = false; s->n_pairs_alloc = 0;
+  s->pending = false; s->pend_obs = nullptr; s->pend_rew = nullptr; s->ev_done = nullptr;
   s->d.sc = *sc; s->d.n_env = n_env; s->d.seed = seed; s->d.first_env_id = 0;
   RsScenario& d = s->d.sc;
   const int L = sc->n_lanes, K = sc->n_links, S = sc->n_signals;
@@ -942,6 +944,7 @@ extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, ui
   s->carveout = ec ? atoi(ec) : -1;
   TRY(configure(s));
   CK(cudaEventCreate(&s->ev0)); CK(cudaEventCreate(&s->ev1));
+  CK(cudaEventCreateWithFlags(&s->ev_done, cudaEventDisableTiming));
   *out = s;
   return rs_reset(s, seed, 0, nullptr);
 }
@@ -955,6 +958,7 @@ extern "C" int rs_destroy(RsSim* s) {
   if (s->h_rew_pinned) cudaFreeHost(s->h_rew_pinned);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
+  if (s->ev_done) cudaEventDestroy(s->ev_done);
   delete s;
   return 0;
 }
@@ -1010,23 +1014,44 @@ static bool is_pinned(const void* p) {
   return a.type == cudaMemoryTypeHost;
 }
 
-extern "C" int rs_env_step_host(RsSim* s, const int32_t* h_actions, float* h_obs, float* h_reward, int32_t reward_kind) {
-  if (!s || !h_actions) return fail(RS_ERR_INVALID, "rs_env_step_host: bad arguments");
+extern "C" int rs_env_step_host_async(RsSim* s, const int32_t* h_actions, float* h_obs, float* h_reward,
+                                      int32_t reward_kind, void* stream) {
+  if (!s || !h_actions) return fail(RS_ERR_INVALID, "rs_env_step_host_async: bad arguments");
+  if (s->pending) return fail(RS_ERR_INVALID, "rs_env_step_host_async: a step is already pending (call rs_wait)");
+  CK(cudaSetDevice(s->device));
+  cudaStream_t st = (cudaStream_t)stream;
   const size_t NS = (size_t)s->d.n_env * s->d.sc.n_signals;
   // page-locked caller buffers are used directly; pageable ones go through the sim's pinned staging buffers
   const bool pa = is_pinned(h_actions), po = !h_obs || is_pinned(h_obs), pr = !h_reward || is_pinned(h_reward);
   const int32_t* src = h_actions;
   if (!pa) { memcpy(s->h_act_pinned, h_actions, sizeof(int32_t) * NS); src = s->h_act_pinned; }
-  CK(cudaMemcpyAsync(s->d_actions, src, sizeof(int32_t) * NS, cudaMemcpyHostToDevice, 0));
-  int r = rs_env_step(s, s->d_actions, nullptr);
+  CK(cudaMemcpyAsync(s->d_actions, src, sizeof(int32_t) * NS, cudaMemcpyHostToDevice, st));
+  int r = rs_env_step(s, s->d_actions, st);
   if (r) return r;
   const float* rew = reward_kind == 0 ? s->d.rew_wait : (reward_kind == 1 ? s->d.rew_wait_norm : s->d.rew_pressure);
-  if (h_obs) CK(cudaMemcpyAsync(po ? h_obs : s->h_obs_pinned, s->d.mplight, sizeof(float) * NS * 13, cudaMemcpyDeviceToHost, 0));
-  if (h_reward) CK(cudaMemcpyAsync(pr ? h_reward : s->h_rew_pinned, rew, sizeof(float) * NS, cudaMemcpyDeviceToHost, 0));
-  CK(cudaStreamSynchronize(0));
-  if (h_obs && !po) memcpy(h_obs, s->h_obs_pinned, sizeof(float) * NS * 13);
-  if (h_reward && !pr) memcpy(h_reward, s->h_rew_pinned, sizeof(float) * NS);
+  if (h_obs) CK(cudaMemcpyAsync(po ? h_obs : s->h_obs_pinned, s->d.mplight, sizeof(float) * NS * 13, cudaMemcpyDeviceToHost, st));
+  if (h_reward) CK(cudaMemcpyAsync(pr ? h_reward : s->h_rew_pinned, rew, sizeof(float) * NS, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(s->ev_done, st));
+  s->pending = true;
+  s->pend_obs = (h_obs && !po) ? h_obs : nullptr;
+  s->pend_rew = (h_reward && !pr) ? h_reward : nullptr;
   return 0;
+}
+
+extern "C" int rs_wait(RsSim* s) {
+  if (!s) return fail(RS_ERR_INVALID, "rs_wait: null sim");
+  if (!s->pending) return 0;
+  s->pending = false;
+  CK(cudaEventSynchronize(s->ev_done));
+  const size_t NS = (size_t)s->d.n_env * s->d.sc.n_signals;
+  if (s->pend_obs) memcpy(s->pend_obs, s->h_obs_pinned, sizeof(float) * NS * 13);
+  if (s->pend_rew) memcpy(s->pend_rew, s->h_rew_pinned, sizeof(float) * NS);
+  return 0;
+}
+
+extern "C" int rs_env_step_host(RsSim* s, const int32_t* h_actions, float* h_obs, float* h_reward, int32_t reward_kind) {
+  int r = rs_env_step_host_async(s, h_actions, h_obs, h_reward, reward_kind, nullptr);
+  return r ? r : rs_wait(s);
 }
 
 extern "C" int rs_policy_maxpressure(RsSim* s, const int32_t* h_pairs, int32_t n_pairs, const int32_t* h_valid,

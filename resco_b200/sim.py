@@ -38,7 +38,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
 
 EXPORTS = ["rs_last_error", "rs_abi_version", "rs_create", "rs_destroy", "rs_reset", "rs_set_phase", "rs_tick",
-           "rs_observe", "rs_env_step", "rs_env_step_host", "rs_policy_maxpressure", "rs_get_obs", "rs_get_stats",
+           "rs_observe", "rs_env_step", "rs_env_step_host", "rs_env_step_host_async", "rs_wait", "rs_policy_maxpressure", "rs_get_obs", "rs_get_stats",
            "rs_dump_vehicles", "rs_get_phases", "rs_get_trip_records", "rs_kernel_launches", "rs_last_step_ms"]
 
 
@@ -61,6 +61,8 @@ def load_library():
     lib.rs_observe.argtypes = [C.c_void_p, C.c_void_p]
     lib.rs_env_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.rs_env_step_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+    lib.rs_env_step_host_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    lib.rs_wait.argtypes = [C.c_void_p]
     lib.rs_policy_maxpressure.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                                           C.c_void_p]
     lib.rs_get_obs.argtypes = [C.c_void_p, C.POINTER(RsObsView)]
@@ -162,21 +164,39 @@ class VecSim:
         self._keep_actions = actions
         _check(self.lib, self.lib.rs_env_step(self._h, actions.data_ptr(), self._stream()))
 
-    def env_step_host(self, actions: np.ndarray, reward_kind: int = 0):
-        """End-to-end call with HOST buffers (H2D actions, D2H mplight obs + reward).  The returned arrays
-        are page-locked buffers owned by this object and are overwritten by the next call."""
+    def _host_buffers(self):
         if getattr(self, "_host_bufs", None) is None:
             t = self._torch
             self._host_bufs = (t.empty((self.n_env, self.S), dtype=t.int32).pin_memory(),
                                t.empty((self.n_env, self.S, 13), dtype=t.float32).pin_memory(),
                                t.empty((self.n_env, self.S), dtype=t.float32).pin_memory())
             self._host_np = tuple(b.numpy() for b in self._host_bufs)
-        act_t, obs_t, rew_t = self._host_bufs
-        act_np, obs_np, rew_np = self._host_np
+        return self._host_bufs, self._host_np
+
+    def env_step_host(self, actions: np.ndarray, reward_kind: int = 0):
+        """End-to-end call with HOST buffers (H2D actions, D2H mplight obs + reward).  The returned arrays
+        are page-locked buffers owned by this object and are overwritten by the next call."""
+        (act_t, obs_t, rew_t), (act_np, obs_np, rew_np) = self._host_buffers()
         np.copyto(act_np, np.asarray(actions).reshape(self.n_env, self.S), casting="unsafe")
         _check(self.lib, self.lib.rs_env_step_host(self._h, act_t.data_ptr(), obs_t.data_ptr(), rew_t.data_ptr(),
                                                    reward_kind))
         return obs_np, rew_np
+
+    def env_step_host_async(self, actions: np.ndarray, reward_kind: int = 0, stream=None):
+        """Enqueue one end-to-end step (H2D actions -> env step -> D2H obs + reward) on `stream` (a raw
+        cudaStream_t / torch stream; default: the current torch stream) and return immediately; `wait()`
+        delivers the results.  Two sims holding half a batch each, stepped alternately, overlap the host
+        agent of one half with the device step of the other."""
+        (act_t, obs_t, rew_t), (act_np, _, _) = self._host_buffers()
+        np.copyto(act_np, np.asarray(actions).reshape(self.n_env, self.S), casting="unsafe")
+        st = self._stream() if stream is None else int(getattr(stream, "cuda_stream", stream))
+        _check(self.lib, self.lib.rs_env_step_host_async(self._h, act_t.data_ptr(), obs_t.data_ptr(),
+                                                         rew_t.data_ptr(), reward_kind, st))
+
+    def wait(self):
+        """Block until the step enqueued by `env_step_host_async` has finished -> (obs, reward) host arrays."""
+        _check(self.lib, self.lib.rs_wait(self._h))
+        return self._host_np[1], self._host_np[2]
 
     def policy_maxpressure(self, pairs, valid_acts, signal_ids, use_wave: bool = False):
         """Batched MAXPRESSURE / MAXWAVE on the device -> [N, S] int32 CUDA tensor of actions."""

@@ -103,6 +103,37 @@ def test_host_step_matches_device_step():
         assert np.array_equal(rew, oo["reward_pressure"])
 
 
+def test_async_half_batches_match_one_batch():
+    """rs_env_step_host_async / rs_wait: two sims holding instances [0,2) and [2,5) on two streams, stepped
+    alternately with a step in flight each, reproduce one 5-instance sim stepped synchronously."""
+    import torch
+    from resco_b200.sim import VecSim
+    sc, m = util.marshal_map("cologne8")
+    full = VecSim(m, 5, seed=11); full.reset(11, 40); full.observe()
+    halves = [VecSim(m, 2, seed=11), VecSim(m, 3, seed=11)]
+    halves[0].reset(11, 40); halves[1].reset(11, 42)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for h in halves:
+        h.observe()
+    torch.cuda.synchronize()
+    acts = [util.cyclic_actions(m, 5, step) for step in range(16)]
+    for h, st, sl in zip(halves, streams, (slice(0, 2), slice(2, 5))):
+        h.env_step_host_async(acts[0][sl], reward_kind=1, stream=st)
+    for step in range(16):
+        ref_obs, ref_rew = full.env_step_host(acts[step], reward_kind=1)
+        for h, st, sl in zip(halves, streams, (slice(0, 2), slice(2, 5))):
+            obs, rew = h.wait()
+            assert np.array_equal(obs, ref_obs[sl]) and np.array_equal(rew, ref_rew[sl]), step
+            if step + 1 < 16:
+                h.env_step_host_async(acts[step + 1][sl], reward_kind=1, stream=st)
+    with pytest.raises(Exception):      # one pending step per sim
+        halves[0].env_step_host_async(acts[0][0:2], stream=streams[0])
+        halves[0].env_step_host_async(acts[0][0:2], stream=streams[0])
+    halves[0].wait()
+    for h in halves + [full]:
+        h.close()
+
+
 def test_synthetic_grid_parity():
     """BASELINE configs[4] shape: synthetic 4x4 grid, Bernoulli(lambda/3600) arrivals per entry lane."""
     from pyoracle import OracleSim
