@@ -322,7 +322,10 @@ static void plan_vehicle(const OrcSim* s, Inst* in, int i, int lane, int rank) {
     float seen = sc->lane_len[lane] - x->pos;
     int cur = lane, cc = x->cursor;
     float la = brake_gap(vacc, decel, 0.0f) + 2.0f * vacc + 5.0f;
-    for (int hop = 0; hop < MAX_HOPS; ++hop) {
+    /* a lane end further away than the look-ahead distance plus the longest vehicle that could still stick
+     * out of the junction cannot bind the speed: no junction logic at all */
+    const int far = seen > la + 20.0f;
+    for (int hop = 0; hop < MAX_HOPS && !far; ++hop) {
       int k = choose_link(sc, cur, x->route, cc);
       if (k == -1) break;                       /* arrival at the end of this lane */
       if (k == -2) {

@@ -254,6 +254,10 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
       int h = hs;
       if (hm >= 0 && (hs < 0 || T.pos[hm] > T.pos[hs])) h = hm;
       if (h < 0) continue;
+      // cheap test first: only a head that could not brake in time is worth the route look-ahead
+      int hvt = v_vtype(T, h);
+      float gap = (__ldg(sc.lane_len + pl) - T.pos[h]) + __ldg(sc.origin_watch_dist + w) - VTT(T, hvt, VT_GAP);
+      if (!(gap < brake_gap(T.speed[h], VTT(T, hvt, VT_DECEL), VTT(T, hvt, VT_TAU)))) continue;
       int cur = pl, cc = v_cursor(T, h), hr = v_route(T, h);
       bool reaches = false;
       for (int hop = 0; hop < 4; ++hop) {
@@ -265,10 +269,7 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
         if (!__ldg(sc.lane_internal + nxt)) cc += 1;
         cur = nxt;
       }
-      if (!reaches) continue;
-      int hvt = v_vtype(T, h);
-      float gap = (__ldg(sc.lane_len + pl) - T.pos[h]) + __ldg(sc.origin_watch_dist + w) - VTT(T, hvt, VT_GAP);
-      if (gap < brake_gap(T.speed[h], VTT(T, hvt, VT_DECEL), VTT(T, hvt, VT_TAU))) ok = false;
+      if (reaches) ok = false;
       }
       if (ok) { c.ok_dd = dd; int s = atomicAdd(&misc[M_NOKC], 1); oklist[s] = (uint16_t)o; atomicAdd(&misc[M_NOK], 1); }
     }

@@ -377,7 +377,10 @@ RS_HEAVY void plan_vehicle(const RsScenario& sc, const Tile& t, int i, float& vn
     float seen = lane_len - x;
     int cur = lane, cc = cursor;
     float la = brake_gap(vacc, decel, 0.0f) + 2.0f * vacc + 5.0f;
-    for (int hop = 0; hop < kMaxHops; ++hop) {
+    // a lane end further away than the look-ahead distance plus the longest vehicle that could still stick
+    // out of the junction cannot bind the speed: no junction logic at all
+    const bool far = seen > la + 20.0f;
+    for (int hop = 0; hop < kMaxHops && !far; ++hop) {
       int k = hop == 0 ? v_nextlink(sc, t, i, lane) : next_link(sc, cur, route, cc);
       if (k == -1) break;
       if (k == -2) {
