@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define RS_ABI_VERSION 1
+#define RS_ABI_VERSION 2
 #define RS_N_MOVEMENTS 12   /* the 12 movement keys of signal_config.py lane_sets */
 
 typedef enum RsStatus {
@@ -39,7 +39,7 @@ typedef struct RsScenario {
   /* sizes */
   int32_t n_lanes, n_edges, n_links, n_foes, n_tls, n_phases, n_state_chars, n_signals;
   int32_t n_sig_lanes, n_mv_lanes, n_mvo, n_out, n_yellow;
-  int32_t n_vtypes, n_routes, n_route_steps, n_origins, n_trips, n_origin_routes, n_watch;
+  int32_t n_vtypes, n_routes, n_route_steps, n_origins, n_trips, n_origin_routes, n_watch, n_lane_watch;
   /* lanes */
   const float* lane_len;
   const float* lane_vmax;
@@ -115,6 +115,10 @@ typedef struct RsScenario {
   const int32_t* origin_watch_lane;
   const float* origin_watch_dist;    /* end of watch lane -> start of origin lane (m) */
   const int32_t* origin_watch_owner; /* [n_watch] origin index of each entry */
+  /* lane-change safety: lanes within 60 m upstream of each lane of a multi-lane edge (empty otherwise) */
+  const int32_t* lane_watch_off;     /* [n_lanes+1] */
+  const int32_t* lane_watch_lane;    /* [n_lane_watch] */
+  const float* lane_watch_dist;      /* end of watch lane -> start of the lane (m) */
   /* parameters */
   int32_t synthetic;
   int32_t synthetic_vtype;

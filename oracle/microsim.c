@@ -26,6 +26,7 @@
  * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off: no FMA contraction, plain IEEE f32).
  */
 #include <math.h>
+#include <stdio.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -233,13 +234,13 @@ static int link_blocked(const OrcSim* s, const Inst* in, int k, float seen, floa
 
 /* stop-line decision for link k seen `seen` metres ahead by vehicle x (hop 0 = the link at the end of
  * its own lane) */
-static int must_stop(const OrcSim* s, const Inst* in, const Veh* x, int k, float seen, int hop, int cursor) {
+static int must_stop(const OrcSim* s, const Inst* in, const Veh* x, int k, float seen, int hop, int cursor, int binds) {
   const RsScenario* sc = &s->sc;
   float len = VT(s, x->vtype, VT_LEN), decel = VT(s, x->vtype, VT_DECEL);
   int from = sc->link_from[k];
   if (sc->lane_internal[from]) {
     int p = sc->link_parent[k];
-    if (hop == 0 && p >= 0 && sc->link_cont[p] && sc->link_via[p] == from)
+    if ((hop == 0 || binds) && p >= 0 && sc->link_cont[p] && sc->link_via[p] == from)
       return link_blocked(s, in, p, seen, x->speed, sc->link_via_len[p] - sc->lane_len[from] + len);
     return 0;
   }
@@ -247,10 +248,14 @@ static int must_stop(const OrcSim* s, const Inst* in, const Veh* x, int k, float
   if (st == 'r' || st == 'u') return 1;
   if (st == 'y' || st == 'Y') return seen >= brake_gap(x->speed, decel, 0.0f) ? 2 : 0;
   if (st == 's' && !(x->wait > 0.0f && seen <= 2.0f)) return 3;
-  if (hop != 0) return 0;
+  /* right of way / keep-clear for a link further ahead only if stopping in front of it would bind the speed
+   * now (short lanes are crossed within one tick, so the link at the end of the own lane is not enough) */
+  if (hop != 0 && !binds) return 0;
   int minor = (st == 'g' || st == 'm' || st == '=' || st == 'Z' || st == 'w' || st == 's' || st == 'o');
   if (sc->link_cont[k]) {
-    if (lane_count(in, sc->link_via[k]) > 0) return 4; /* waiting slot inside the junction is taken */
+    /* waiting slot inside the junction is taken by a STANDING vehicle (a moving one is simply followed) */
+    int vl = sc->link_via[k];
+    if (lane_count(in, vl) > 0 && in->veh[in->lane_start[vl + 1] - 1].speed < HALT_SPEED) return 4;
   } else if (minor) {
     int b = link_blocked(s, in, k, seen, x->speed, sc->link_via_len[k] + len);
     if (b) return b;
@@ -260,15 +265,31 @@ static int must_stop(const OrcSim* s, const Inst* in, const Veh* x, int k, float
       if (li >= 0 && lane_count(in, li) > 0) return 400000 + sc->foe_link[fi];
     }
   }
-  /* keep the junction clear: enter only if the vehicle fits behind whatever stands beyond it */
-  {
+  /* keep the junction clear (SUMO MSVehicle::keepClear / checkRewindLinkLanes / MSLane::getSpaceTillLastStanding):
+   * only links with foes, and only when a vehicle was seen beyond the stop line.  Space = room behind the last
+   * STANDING vehicle of the lanes ahead (moving vehicles only take their own length), minus the vehicles that are
+   * already inside this junction on my path; lanes are added up to the first standing vehicle / red light. */
+  if (sc->link_foe_off[k + 1] > sc->link_foe_off[k]) {
     float need = len + VT(s, x->vtype, VT_GAP), space = 0.0f;
-    int cur = sc->link_to[k], cc2 = cursor + 1;
+    int had = 0, cc2 = cursor + 1;
+    int cur = sc->link_via[k] >= 0 ? sc->link_via[k] : sc->link_to[k];
+    for (int h = 0; h < 3 && sc->lane_internal[cur]; ++h) {     /* my own path through the junction */
+      if (lane_count(in, cur) > 0) { had = 1; space -= in->lane_occ[cur]; }
+      int k2 = sc->lane_link_off[cur];
+      cur = sc->link_via[k2] >= 0 ? sc->link_via[k2] : sc->link_to[k2];
+    }
     for (int h = 0; h < 6; ++h) {
-      float free_room = sc->lane_len[cur] - in->lane_occ[cur]; /* length not covered by vehicles (+ their gaps) */
-      if (free_room > 0.0f) space += free_room;
+      int a = in->lane_start[cur], j = in->lane_start[cur + 1] - 1, stopped = 0;
+      float lengths = 0.0f;
+      if (j >= a) had = 1;
+      for (; j >= a; --j) {                                      /* from the tail forward */
+        const Veh* y = &in->veh[j];
+        if (y->speed < HALT_SPEED) { stopped = 1; break; }
+        lengths += VT(s, y->vtype, VT_LEN) + VT(s, y->vtype, VT_GAP);
+      }
+      if (stopped) { space += (in->veh[j].pos - VT(s, in->veh[j].vtype, VT_LEN)) - lengths; break; }
+      if (!sc->lane_internal[cur]) space += sc->lane_len[cur] - lengths;   /* junction interiors are no place to stand */
       if (space >= need) return 0;
-      if (lane_count(in, cur) > 0) break;
       int k2 = choose_link(sc, cur, x->route, cc2);
       if (k2 < 0) return 0;
       if (!sc->lane_internal[cur]) {
@@ -278,7 +299,7 @@ static int must_stop(const OrcSim* s, const Inst* in, const Veh* x, int k, float
       cur = sc->link_via[k2] >= 0 ? sc->link_via[k2] : sc->link_to[k2];
       if (!sc->lane_internal[cur]) cc2 += 1;
     }
-    if (space < need) return 7;
+    if (had && space < need) return 7;
   }
   return 0;
 }
@@ -333,7 +354,8 @@ static void plan_vehicle(const OrcSim* s, Inst* in, int i, int lane, int rank) {
         if (hop == 0) wrong_lane_head = 1;
         break;
       }
-      if (must_stop(s, in, x, k, seen, hop, cc)) { vsafe = fminf(vsafe, max_safe_stop_speed(seen, decel, tau)); break; }
+      float vstop = max_safe_stop_speed(seen, decel, tau);
+      if (must_stop(s, in, x, k, seen, hop, cc, vstop < vsafe)) { vsafe = fminf(vsafe, vstop); break; }
       int nxt = sc->link_via[k] >= 0 ? sc->link_via[k] : sc->link_to[k];
       vsafe = fminf(vsafe, free_speed(decel, seen, fminf(sc->lane_vmax[nxt] * x->sf, vcap)));
       if (lane_count(in, nxt) > 0) {
@@ -347,6 +369,29 @@ static void plan_vehicle(const OrcSim* s, Inst* in, int i, int lane, int rank) {
       if (!sc->lane_internal[nxt]) cc += 1;
       cur = nxt;
       if (seen > la) break;
+    }
+  }
+  /* ---- cooperation (LC2013 informFollower analogue): a vehicle of the neighbouring lane that MUST get into
+   * this lane (its lane does not lead on) and is urgent becomes a virtual leader for everybody behind it ---- */
+  if (sc->lane_change && !sc->lane_internal[lane]) {
+    for (int side = 0; side < 2; ++side) {
+      int nl = side == 0 ? sc->lane_left[lane] : sc->lane_right[lane];
+      if (nl < 0) continue;
+      int a = in->lane_start[nl], j = in->lane_start[nl + 1] - 1;
+      float gapu = 0.0f;
+      for (; j >= a; --j) {               /* from the tail forward: first vehicle that is entirely ahead of me */
+        gapu = in->veh[j].pos - VT(s, in->veh[j].vtype, VT_LEN) - x->pos - mingap;
+        if (gapu >= 0.0f) break;
+      }
+      if (j < a) continue;
+      const Veh* u = &in->veh[j];
+      int masku = sc->route_mask[sc->route_off[u->route] + u->cursor];
+      if ((masku >> sc->lane_index[nl]) & 1) continue;                       /* its lane leads on: not urgent */
+      if (!(sc->lane_len[nl] - u->pos < 60.0f || u->wait > 3.0f)) continue;
+      int du = strategic_dir(sc, u, nl);
+      if ((du > 0 ? sc->lane_left[nl] : (du < 0 ? sc->lane_right[nl] : -1)) != lane) continue;
+      if (!(sc->lane_perm[lane] & sc->vtype_bit[u->vtype])) continue;
+      vsafe = fminf(vsafe, follow_speed(gapu, u->speed, VT(s, u->vtype, VT_DECEL), decel, tau));
     }
   }
   float vmin_n = fmaxf(0.0f, v - decel);
@@ -367,24 +412,29 @@ static void plan_vehicle(const OrcSim* s, Inst* in, int i, int lane, int rank) {
     int ro = sc->route_off[x->route];
     int mask = sc->route_mask[ro + x->cursor];
     int bestm = (mask >> 8) & 0xFF;
-    int dir = strategic_dir(sc, x, lane), strategic = dir != 0;
+    int okm = mask & 0xFF, myidx = sc->lane_index[lane];
+    int dir = strategic_dir(sc, x, lane);
+    /* strategic (must): the route cannot continue from this lane.  A lane that leads on but is not "best"
+     * only makes the best lanes attractive (no speed loss needed to go there); any lane that leads on may be
+     * used to get around a blocked leader. */
+    int strategic = dir != 0 && !((okm >> myidx) & 1);
+    int cur_best = (bestm >> myidx) & 1;
     /* urgent: the route cannot continue from this lane and the lane end is near (or the vehicle already
      * stands): accept any gap the neighbours can still handle with emergency braking */
-    int urgent = strategic && !((mask >> sc->lane_index[lane]) & 1) &&
-                 (sc->lane_len[lane] - x->pos < 60.0f || x->wait > 3.0f);
+    int urgent = strategic && (sc->lane_len[lane] - x->pos < 60.0f || x->wait > 3.0f);
     for (int pass = 0; pass < 2; ++pass) {
-      /* pass 0: strategic direction (if any); pass 1 (no strategic need): speed gain, left then right */
+      /* pass 0: strategic direction (if any); otherwise both directions, left then right */
       int d;
       if (strategic) { if (pass) break; d = dir; }
       else {
-        if (x->lcc > 0 || !(vlead_limit < vacc - 1.0f)) break;
+        if (x->lcc > 0 || (cur_best && !(vlead_limit < vacc - 1.0f))) break;
         d = pass == 0 ? 1 : -1;
       }
       if (d == 0) break;
       if ((d > 0) == ((in->tick & 1) != 0)) continue; /* even ticks: leftward, odd ticks: rightward */
       int nl = d > 0 ? sc->lane_left[lane] : sc->lane_right[lane];
       if (nl < 0 || !(sc->lane_perm[nl] & sc->vtype_bit[vt])) continue;
-      if (!strategic && !((bestm >> sc->lane_index[nl]) & 1)) continue;
+      if (!strategic && !((okm >> sc->lane_index[nl]) & 1)) continue;
       /* neighbours in nl: leader = last with pos >= mine, follower = first with pos < mine */
       int a = in->lane_start[nl], b = in->lane_start[nl + 1], j = a;
       while (j < b && in->veh[j].pos >= x->pos) ++j;
@@ -404,14 +454,45 @@ static void plan_vehicle(const OrcSim* s, Inst* in, int i, int lane, int rank) {
         float gap = x->pos - len - fo->pos - VT(s, fo->vtype, VT_GAP);
         if (gap < 0.0f) ok = 0;
         else if (urgent) {
-          if (gap < brake_gap(fo->speed, fmaxf(VT(s, fo->vtype, VT_DECEL), EMERGENCY_DECEL), 0.0f)) ok = 0;
+          if (gap < brake_gap(fo->speed, fmaxf(VT(s, fo->vtype, VT_DECEL), EMERGENCY_DECEL), 1.0f)) ok = 0;   /* 1 s: it reacts a tick late */
         } else {
           float vf = follow_speed(gap, v, decel, VT(s, fo->vtype, VT_DECEL), VT(s, fo->vtype, VT_TAU));
           if (vf < fo->speed + VT(s, fo->vtype, VT_ACCEL) - VT(s, fo->vtype, VT_DECEL)) ok = 0;
         }
       }
+      /* nobody behind in the target lane: the follower may still be upstream of it, about to come out of a junction */
+      if (ok && j >= b && x->pos - len < 60.0f) {
+        for (int w = sc->lane_watch_off[nl]; ok && w < sc->lane_watch_off[nl + 1]; ++w) {
+          int pl = sc->lane_watch_lane[w];
+          if (lane_count(in, pl) == 0) continue;
+          const Veh* h = &in->veh[in->lane_start[pl]];
+          float gap = (x->pos - len) + sc->lane_watch_dist[w] + (sc->lane_len[pl] - h->pos) - VT(s, h->vtype, VT_GAP);
+          int unsafe;
+          if (urgent) unsafe = gap < brake_gap(h->speed, fmaxf(VT(s, h->vtype, VT_DECEL), EMERGENCY_DECEL), 1.0f);
+          else {
+            float vf = follow_speed(gap, v, decel, VT(s, h->vtype, VT_DECEL), VT(s, h->vtype, VT_TAU));
+            unsafe = vf < h->speed + VT(s, h->vtype, VT_ACCEL) - VT(s, h->vtype, VT_DECEL);
+          }
+          if (!unsafe) continue;
+          int cur = pl, cc = h->cursor;          /* does its route lead onto the target lane? */
+          for (int hop = 0; hop < 4; ++hop) {
+            int k = choose_link(sc, cur, h->route, cc);
+            if (k < 0) break;
+            int nxt = sc->link_via[k] >= 0 ? sc->link_via[k] : sc->link_to[k];
+            if (nxt == nl) { ok = 0; break; }
+            if (!sc->lane_internal[nxt]) cc += 1;
+            cur = nxt;
+          }
+        }
+      }
       if (!ok) continue;
-      if (!strategic && !(fminf(vfol, vacc) > vlead_limit + 1.0f)) continue;
+      if (!strategic) {   /* required speed gain: none towards a best lane, 1 m/s between best lanes, 2 m/s away from them */
+        int nl_best = (bestm >> sc->lane_index[nl]) & 1;
+        float gain = fminf(vfol, vacc) - vlead_limit;
+        if (nl_best && !cur_best) { if (!(gain >= -0.5f)) continue; }
+        else if (nl_best) { if (!(gain > 1.0f)) continue; }
+        else if (!(gain > 2.0f && vlead_limit < vacc - 1.0f)) continue;
+      }
       target = nl;
       vn = fmaxf(0.0f, fminf(vn, vfol));
       break;
@@ -636,10 +717,25 @@ static void tick_instance(OrcSim* s, Inst* in) {
     in->n_veh = w;
     free(add); free(newv); free(newl);
   }
+  if (getenv("ORC_TRACE")) {   /* diagnostic: ORC_TRACE="vidA,vidB" prints both vehicles every tick */
+    int va = -1, vb = -1;
+    sscanf(getenv("ORC_TRACE"), "%d,%d", &va, &vb);
+    for (int l = 0; l < L; ++l)
+      for (int i = in->lane_start[l]; i < in->lane_start[l + 1]; ++i)
+        if (in->veh[i].vid == va || in->veh[i].vid == vb)
+          fprintf(stderr, "[trace] env %llu tick %d vid %d lane %d pos %.3f v %.3f wait %.0f\n", (unsigned long long)in->env_id,
+                  in->tick, in->veh[i].vid, l, in->veh[i].pos, in->veh[i].speed, in->veh[i].wait);
+  }
   /* ordering anomaly check (diagnostic; stays 0 when the rules keep vehicles apart) */
   for (int l = 0; l < L; ++l)
     for (int i = in->lane_start[l] + 1; i < in->lane_start[l + 1]; ++i)
-      if (in->veh[i].pos > in->veh[i - 1].pos) in->st.anomalies += 1;
+      if (in->veh[i].pos > in->veh[i - 1].pos) {
+        in->st.anomalies += 1;
+        if (getenv("ORC_DEBUG"))
+          fprintf(stderr, "[oracle] ordering anomaly: env %llu tick %d lane %d: vid %d pos %.3f v %.3f behind vid %d pos %.3f v %.3f\n",
+                  (unsigned long long)in->env_id, in->tick, l, in->veh[i].vid, in->veh[i].pos, in->veh[i].speed,
+                  in->veh[i - 1].vid, in->veh[i - 1].pos, in->veh[i - 1].speed);
+      }
   if (sc->synthetic)
     for (int o = 0; o < sc->n_origins; ++o) in->st.sum_delay_pending += (float)in->origin_backlog[o];
   in->st.sum_active_ticks += in->n_veh;
@@ -769,6 +865,7 @@ OrcSim* orc_create(const RsScenario* sc, int32_t n_env, uint64_t seed) {
   DUP(origin_rate, sc->n_origins, int32_t); DUP(origin_route_off, sc->n_origins + 1, int32_t);
   DUP(origin_route, sc->n_origin_routes, int32_t);
   DUP(origin_watch_off, sc->n_origins + 1, int32_t); DUP(origin_watch_lane, sc->n_watch, int32_t); DUP(origin_watch_dist, sc->n_watch, float); DUP(origin_watch_owner, sc->n_watch, int32_t);
+  DUP(lane_watch_off, L + 1, int32_t); DUP(lane_watch_lane, sc->n_lane_watch, int32_t); DUP(lane_watch_dist, sc->n_lane_watch, float);
   s->inst = (Inst*)calloc((size_t)n_env, sizeof(Inst));
   int V = sc->vcap, SL = sc->n_sig_lanes;
   for (int e = 0; e < n_env; ++e) {
@@ -943,7 +1040,7 @@ void orc_explain(OrcSim* s, int32_t env, int32_t lane, int32_t* out) {
     out[0] = k; out[2] = hop; out[3] = (int)(seen * 100.0f);
     if (k == -1) { out[1] = -1; return; }
     if (k == -2) { out[1] = 8; return; }
-    int r = must_stop(s, in, x, k, seen, hop, cc);
+    int r = must_stop(s, in, x, k, seen, hop, cc, 1);
     if (r) { out[1] = r; return; }
     int nxt = sc->link_via[k] >= 0 ? sc->link_via[k] : sc->link_to[k];
     if (lane_count(in, nxt) > 0) { out[1] = 9; out[0] = nxt; return; }

@@ -12,7 +12,7 @@ import numpy as np
 
 from .scenario.compiler import Scenario, green_phase_indices
 
-RS_ABI_VERSION = 1
+RS_ABI_VERSION = 2
 
 _I32P = C.POINTER(C.c_int32)
 _F32P = C.POINTER(C.c_float)
@@ -20,7 +20,7 @@ _U8P = C.POINTER(C.c_uint8)
 
 _SIZES = ["n_lanes", "n_edges", "n_links", "n_foes", "n_tls", "n_phases", "n_state_chars", "n_signals",
           "n_sig_lanes", "n_mv_lanes", "n_mvo", "n_out", "n_yellow",
-          "n_vtypes", "n_routes", "n_route_steps", "n_origins", "n_trips", "n_origin_routes", "n_watch"]
+          "n_vtypes", "n_routes", "n_route_steps", "n_origins", "n_trips", "n_origin_routes", "n_watch", "n_lane_watch"]
 
 _PTRS: List[Tuple[str, object]] = [
     ("lane_len", _F32P), ("lane_vmax", _F32P), ("lane_edge", _I32P), ("lane_index", _I32P),
@@ -43,6 +43,7 @@ _PTRS: List[Tuple[str, object]] = [
     ("origin_rate", _I32P), ("origin_route_off", _I32P), ("origin_route", _I32P),
     ("origin_watch_off", _I32P), ("origin_watch_lane", _I32P), ("origin_watch_dist", _F32P),
     ("origin_watch_owner", _I32P),
+    ("lane_watch_off", _I32P), ("lane_watch_lane", _I32P), ("lane_watch_dist", _F32P),
 ]
 
 _PARAMS = [("synthetic", C.c_int32), ("synthetic_vtype", C.c_int32), ("step_length", C.c_int32),
@@ -212,7 +213,7 @@ def marshal(sc: Scenario, *, step_length: int = 10, yellow_length: int = 3, max_
         n_out=len(a["out_sig"]) if controlled else 0, n_yellow=len(yellow_idx),
         n_vtypes=len(a["vtype_bit"]), n_routes=len(a["route_off"]) - 1, n_route_steps=len(a["route_edge"]),
         n_origins=len(a["origin_lane"]), n_trips=n_trips, n_origin_routes=0,
-        n_watch=len(a["origin_watch_lane"]))
+        n_watch=len(a["origin_watch_lane"]), n_lane_watch=len(a["lane_watch_lane"]))
     arrays: Dict[str, Tuple[object, object]] = {}
     for name, ct in _PTRS:
         if name in a:

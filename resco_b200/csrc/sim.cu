@@ -898,6 +898,8 @@ extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, ui
   TRY(dev_dup(s, d.origin_route, sc->n_origin_routes));
   TRY(dev_dup(s, d.origin_watch_off, sc->n_origins + 1)); TRY(dev_dup(s, d.origin_watch_lane, sc->n_watch));
   TRY(dev_dup(s, d.origin_watch_dist, sc->n_watch)); TRY(dev_dup(s, d.origin_watch_owner, sc->n_watch));
+  TRY(dev_dup(s, d.lane_watch_off, sc->n_lanes + 1)); TRY(dev_dup(s, d.lane_watch_lane, sc->n_lane_watch));
+  TRY(dev_dup(s, d.lane_watch_dist, sc->n_lane_watch));
   const size_t N = (size_t)n_env;
   TRY(dev_alloc(s, s->d.hdr, N * kHdrInts));
   TRY(dev_alloc(s, s->d.tls_phase, N * sc->n_tls)); TRY(dev_alloc(s, s->d.tls_end, N * sc->n_tls));

@@ -279,8 +279,10 @@ __device__ __forceinline__ float lane_occ(const Tile& t, int l) {
   return occ;
 }
 
-// stop-line decision for link k, `seen` metres ahead of vehicle i (hop 0 = the link at the end of its lane)
-RS_HEAVY bool must_stop(const RsScenario& sc, const Tile& t, int i, int k, float seen, int hop, int cursor) {
+// stop-line decision for link k, `seen` metres ahead of vehicle i (hop 0 = the link at the end of its lane).
+// `binds`: stopping in front of the link would bind the speed now -- right of way and keep-clear of a link further
+// ahead are only evaluated then (short lanes are crossed within one tick, so hop 0 alone is not enough).
+RS_HEAVY bool must_stop(const RsScenario& sc, const Tile& t, int i, int k, float seen, int hop, int cursor, bool binds) {
   int vt = v_vtype(t, i);
   float len = VTT(t, vt, VT_LEN), decel = VTT(t, vt, VT_DECEL);
   float v = t.speed[i];
@@ -291,7 +293,7 @@ RS_HEAVY bool must_stop(const RsScenario& sc, const Tile& t, int i, int k, float
   int st = 0;
   if (from_internal) {
     int p = __ldg(sc.link_parent + k);
-    if (!(hop == 0 && p >= 0 && __ldg(sc.link_cont + p) && __ldg(sc.link_via + p) == from)) return false;
+    if (!((hop == 0 || binds) && p >= 0 && __ldg(sc.link_cont + p) && __ldg(sc.link_via + p) == from)) return false;
     yield_link = p;
     cross = __ldg(sc.link_via_len + p) - __ldg(sc.lane_len + from) + len;
   } else {
@@ -299,7 +301,7 @@ RS_HEAVY bool must_stop(const RsScenario& sc, const Tile& t, int i, int k, float
     if (st == 'r' || st == 'u') return true;
     if (st == 'y' || st == 'Y') return seen >= brake_gap(v, decel, 0.0f);
     if (st == 's' && !(v_wait(t, i) > 0 && seen <= 2.0f)) return true;
-    if (hop != 0) return false;
+    if (hop != 0 && !binds) return false;
     bool minor = (st == 'g' || st == 'm' || st == '=' || st == 'Z' || st == 'w' || st == 's' || st == 'o');
     if (!__ldg(sc.link_cont + k) && minor) { yield_link = k; cross = __ldg(sc.link_via_len + k) + len; }
   }
@@ -308,27 +310,50 @@ RS_HEAVY bool must_stop(const RsScenario& sc, const Tile& t, int i, int k, float
     if (from_internal) return b;
     if (b) return true;
   }
+  const int f0 = __ldg(sc.link_foe_off + k), f1 = __ldg(sc.link_foe_off + k + 1);
   if (__ldg(sc.link_cont + k)) {
-    if (lane_count(t, __ldg(sc.link_via + k)) > 0) return true;   // waiting slot inside the junction is taken
+    // waiting slot inside the junction is taken by a STANDING vehicle (a moving one is simply followed)
+    int vl = __ldg(sc.link_via + k);
+    if (lane_count(t, vl) > 0 && t.speed[(int)t.lane_start[vl + 1] - 1] < kHaltSpeed) return true;
   } else if (yield_link < 0) {
-    int f0 = __ldg(sc.link_foe_off + k), f1 = __ldg(sc.link_foe_off + k + 1);
     for (int fi = f0; fi < f1; ++fi) {
       int li = __ldg(sc.link_last_int + __ldg(sc.foe_link + fi));
       if (li >= 0 && lane_count(t, li) > 0) return true;
     }
   }
-  // keep the junction clear: enter only if the vehicle fits behind whatever stands beyond it
+  // keep the junction clear (SUMO keepClear / getSpaceTillLastStanding): only links with foes, and only when a
+  // vehicle was seen beyond the stop line.  Space = room behind the last STANDING vehicle of the lanes ahead (moving
+  // vehicles only take their own length), minus the vehicles already inside this junction on my path.
+  if (f1 <= f0) return false;
   float need = len + VTT(t, vt, VT_GAP), space = 0.0f;
-  int cur = __ldg(sc.link_to + k), cc2 = cursor + 1;
+  bool had = false;
+  int cc2 = cursor + 1;
   int route = v_route(t, i);
+  int cur;
+  { int via = __ldg(sc.link_via + k); cur = via >= 0 ? via : __ldg(sc.link_to + k); }
+  for (int h = 0; h < 3 && __ldg(sc.lane_internal + cur); ++h) {   // my own path through the junction
+    if (lane_count(t, cur) > 0) { had = true; space -= lane_occ(t, cur); }
+    int k2 = __ldg(sc.lane_link_off + cur);
+    int via2 = __ldg(sc.link_via + k2);
+    cur = via2 >= 0 ? via2 : __ldg(sc.link_to + k2);
+  }
   for (int h = 0; h < 6; ++h) {
-    float free_room = __ldg(sc.lane_len + cur) - lane_occ(t, cur);
-    if (free_room > 0.0f) space += free_room;
+    int a = t.lane_start[cur], j = (int)t.lane_start[cur + 1] - 1;
+    bool stopped = false;
+    float lengths = 0.0f;
+    if (j >= a) had = true;
+    for (; j >= a; --j) {                                          // from the tail forward
+      if (t.speed[j] < kHaltSpeed) { stopped = true; break; }
+      int yvt = v_vtype(t, j);
+      lengths += VTT(t, yvt, VT_LEN) + VTT(t, yvt, VT_GAP);
+    }
+    if (stopped) { space += (t.pos[j] - VTT(t, v_vtype(t, j), VT_LEN)) - lengths; break; }
+    const bool cur_internal = __ldg(sc.lane_internal + cur) != 0;
+    if (!cur_internal) space += __ldg(sc.lane_len + cur) - lengths;   // junction interiors are no place to stand
     if (space >= need) return false;
-    if (lane_count(t, cur) > 0) break;
     int k2 = next_link(sc, cur, route, cc2);
     if (k2 < 0) return false;
-    if (!__ldg(sc.lane_internal + cur)) {
+    if (!cur_internal) {
       int st2 = state_now(sc, t, k2);
       if (st2 == 'r' || st2 == 'u' || st2 == 'y') break;
     }
@@ -336,7 +361,7 @@ RS_HEAVY bool must_stop(const RsScenario& sc, const Tile& t, int i, int k, float
     cur = via2 >= 0 ? via2 : __ldg(sc.link_to + k2);
     if (!__ldg(sc.lane_internal + cur)) cc2 += 1;
   }
-  return space < need;
+  return had && space < need;
 }
 
 __device__ __forceinline__ int strategic_dir(const RsScenario& sc, int route, int cursor, int lane) {
@@ -388,7 +413,8 @@ RS_HEAVY void plan_vehicle(const RsScenario& sc, const Tile& t, int i, float& vn
         if (hop == 0) wrong_lane_head = true;
         break;
       }
-      if (must_stop(sc, t, i, k, seen, hop, cc)) { vsafe = fminf(vsafe, max_safe_stop_speed(seen, decel, tau)); break; }
+      const float vstop = max_safe_stop_speed(seen, decel, tau);
+      if (must_stop(sc, t, i, k, seen, hop, cc, vstop < vsafe)) { vsafe = fminf(vsafe, vstop); break; }
       int via = __ldg(sc.link_via + k);
       int nxt = via >= 0 ? via : __ldg(sc.link_to + k);
       vsafe = fminf(vsafe, free_speed(decel, seen, fminf(__ldg(sc.lane_vmax + nxt) * sf, vcapv)));
@@ -406,6 +432,33 @@ RS_HEAVY void plan_vehicle(const RsScenario& sc, const Tile& t, int i, float& vn
       if (seen > la) break;
     }
   }
+  int left = __ldg(sc.lane_left + lane), right = __ldg(sc.lane_right + lane);
+  bool internal = __ldg(sc.lane_internal + lane) != 0;
+  // cooperation (LC2013 informFollower analogue): a vehicle of the neighbouring lane that MUST get into this lane
+  // (its lane does not lead on) and is urgent becomes a virtual leader for everybody behind it
+  if (sc.lane_change && !internal) {
+#pragma unroll 1
+    for (int side = 0; side < 2; ++side) {
+      const int nl = side == 0 ? left : right;
+      if (nl < 0) continue;
+      const int a = t.lane_start[nl];
+      int j = (int)t.lane_start[nl + 1] - 1;
+      float gapu = 0.0f;
+      for (; j >= a; --j) {               // from the tail forward: first vehicle that is entirely ahead of me
+        gapu = t.pos[j] - VTT(t, v_vtype(t, j), VT_LEN) - x - mingap;
+        if (gapu >= 0.0f) break;
+      }
+      if (j < a) continue;
+      const int ur = v_route(t, j), uc = v_cursor(t, j), uvt = v_vtype(t, j);
+      const int masku = __ldg(sc.route_mask + __ldg(sc.route_off + ur) + uc);
+      if ((masku >> __ldg(sc.lane_index + nl)) & 1) continue;                      // its lane leads on: not urgent
+      if (!(__ldg(sc.lane_len + nl) - t.pos[j] < 60.0f || v_wait(t, j) > 3)) continue;
+      const int du = strategic_dir(sc, ur, uc, nl);
+      if ((du > 0 ? __ldg(sc.lane_left + nl) : (du < 0 ? __ldg(sc.lane_right + nl) : -1)) != lane) continue;
+      if (!(__ldg(sc.lane_perm + lane) & __ldg(sc.vtype_bit + uvt))) continue;
+      vsafe = fminf(vsafe, follow_speed(gapu, t.speed[j], VTT(t, uvt, VT_DECEL), decel, tau));
+    }
+  }
   float vmin_n = fmaxf(0.0f, v - decel);
   float vmin_e = fmaxf(0.0f, v - fmaxf(decel, kEmergencyDecel));
   float vmin = fminf(vmin_n, fmaxf(vsafe, vmin_e));
@@ -418,30 +471,32 @@ RS_HEAVY void plan_vehicle(const RsScenario& sc, const Tile& t, int i, float& vn
     vn = fmaxf(vmin, dawdle(vcand, accel, sigma, xi));
   }
   int target = -1;
-  int left = __ldg(sc.lane_left + lane), right = __ldg(sc.lane_right + lane);
-  bool internal = __ldg(sc.lane_internal + lane) != 0;
   if (sc.lane_change && !internal && (left >= 0 || right >= 0) && x + vn <= lane_len) {
     int mask = __ldg(sc.route_mask + __ldg(sc.route_off + route) + cursor);
-    int bestm = (mask >> 8) & 0xFF;
+    int okm = mask & 0xFF, bestm = (mask >> 8) & 0xFF, myidx = __ldg(sc.lane_index + lane);
     int dir = strategic_dir(sc, route, cursor, lane);
-    bool strategic = dir != 0;
+    // strategic (must): the route cannot continue from this lane.  A lane that leads on but is not "best" only
+    // makes the best lanes attractive (no speed loss needed to go there); any lane that leads on may be used to get
+    // around a blocked leader.
+    const bool strategic = dir != 0 && !((okm >> myidx) & 1);
+    const bool cur_best = (bestm >> myidx) & 1;
     // urgent: the route cannot continue from this lane and the lane end is near (or the vehicle already
     // stands): accept any gap the neighbours can still handle with emergency braking
-    const bool urgent = strategic && !((mask >> __ldg(sc.lane_index + lane)) & 1) &&
-                        (lane_len - x < 60.0f || v_wait(t, i) > 3);
+    const bool urgent = strategic && (lane_len - x < 60.0f || v_wait(t, i) > 3);
     int vbit = __ldg(sc.vtype_bit + vt);
     for (int pass = 0; pass < 2; ++pass) {
       int d;
       if (strategic) { if (pass) break; d = dir; }
       else {
-        if (v_lcc(t, i) > 0 || !(vlead_limit < vacc - 1.0f)) break;
+        if (v_lcc(t, i) > 0 || (cur_best && !(vlead_limit < vacc - 1.0f))) break;
         d = pass == 0 ? 1 : -1;
       }
       if (d == 0) break;
       if ((d > 0) == ((t.tick & 1) != 0)) continue;   // even ticks: leftward, odd ticks: rightward
       int nl = d > 0 ? left : right;
       if (nl < 0 || !(__ldg(sc.lane_perm + nl) & vbit)) continue;
-      if (!strategic && !((bestm >> __ldg(sc.lane_index + nl)) & 1)) continue;
+      const int nlidx = __ldg(sc.lane_index + nl);
+      if (!strategic && !((okm >> nlidx) & 1)) continue;
       int a = t.lane_start[nl], b = t.lane_start[nl + 1], j = a;
       while (j < b && t.pos[j] >= x) ++j;
       float vfol = vacc;
@@ -460,14 +515,48 @@ RS_HEAVY void plan_vehicle(const RsScenario& sc, const Tile& t, int i, float& vn
         float gap = x - len - t.pos[j] - VTT(t, fvt, VT_GAP);
         if (gap < 0.0f) ok = false;
         else if (urgent) {
-          if (gap < brake_gap(t.speed[j], fmaxf(VTT(t, fvt, VT_DECEL), kEmergencyDecel), 0.0f)) ok = false;
+          if (gap < brake_gap(t.speed[j], fmaxf(VTT(t, fvt, VT_DECEL), kEmergencyDecel), 1.0f)) ok = false;   // 1 s: it reacts a tick late
         } else {
           float vf = follow_speed(gap, v, decel, VTT(t, fvt, VT_DECEL), VTT(t, fvt, VT_TAU));
           if (vf < t.speed[j] + VTT(t, fvt, VT_ACCEL) - VTT(t, fvt, VT_DECEL)) ok = false;
         }
       }
+      // nobody behind in the target lane: the follower may still be upstream of it, about to come out of a junction
+      if (ok && j >= b && x - len < 60.0f) {
+        const int w1 = __ldg(sc.lane_watch_off + nl + 1);
+        for (int w = __ldg(sc.lane_watch_off + nl); ok && w < w1; ++w) {
+          const int pl = __ldg(sc.lane_watch_lane + w);
+          if (lane_count(t, pl) == 0) continue;
+          const int h = t.lane_start[pl], hvt = v_vtype(t, h);
+          const float gap = (x - len) + __ldg(sc.lane_watch_dist + w) + (__ldg(sc.lane_len + pl) - t.pos[h]) - VTT(t, hvt, VT_GAP);
+          bool unsafe;
+          if (urgent) unsafe = gap < brake_gap(t.speed[h], fmaxf(VTT(t, hvt, VT_DECEL), kEmergencyDecel), 1.0f);
+          else {
+            const float vf = follow_speed(gap, v, decel, VTT(t, hvt, VT_DECEL), VTT(t, hvt, VT_TAU));
+            unsafe = vf < t.speed[h] + VTT(t, hvt, VT_ACCEL) - VTT(t, hvt, VT_DECEL);
+          }
+          if (!unsafe) continue;
+          int cur = pl, cc = v_cursor(t, h);      // does its route lead onto the target lane?
+          const int hr = v_route(t, h);
+          for (int hop = 0; hop < 4; ++hop) {
+            const int k = hop == 0 ? v_nextlink(sc, t, h, pl) : next_link(sc, cur, hr, cc);
+            if (k < 0) break;
+            const int via = __ldg(sc.link_via + k);
+            const int nxt = via >= 0 ? via : __ldg(sc.link_to + k);
+            if (nxt == nl) { ok = false; break; }
+            if (!__ldg(sc.lane_internal + nxt)) cc += 1;
+            cur = nxt;
+          }
+        }
+      }
       if (!ok) continue;
-      if (!strategic && !(fminf(vfol, vacc) > vlead_limit + 1.0f)) continue;
+      if (!strategic) {   // required speed gain: none towards a best lane, 1 m/s between best lanes, 2 m/s away from them
+        const bool nl_best = (bestm >> nlidx) & 1;
+        const float gain = fminf(vfol, vacc) - vlead_limit;
+        if (nl_best && !cur_best) { if (!(gain >= -0.5f)) continue; }
+        else if (nl_best) { if (!(gain > 1.0f)) continue; }
+        else if (!(gain > 2.0f && vlead_limit < vacc - 1.0f)) continue;
+      }
       target = nl;
       vn = fmaxf(0.0f, fminf(vn, vfol));
       break;

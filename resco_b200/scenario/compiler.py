@@ -258,28 +258,49 @@ def compile_net(net: Net) -> Tuple[Dict[str, np.ndarray], Dict[str, object], Dic
 class Router:
     """Shortest travel-time routing for ``<trip from= to=>`` demand.
 
-    SUMO routes trips at load time with Dijkstra on ``length / speed``; tie-breaking in SUMO
-    is not documented, here ties resolve to the lower edge index (deterministic).
+    SUMO routes trips at load time with Dijkstra on travel time: ``length / speed`` of the normal and of the
+    internal edges plus ``weights.minor-penalty`` on unsignalised minor links; tie-breaking in SUMO is not
+    documented, here ties resolve to the lower edge index (deterministic).
     """
 
     def __init__(self, arrays: Dict[str, np.ndarray], n_edges: int):
         self.a = arrays
         self.E = n_edges
         a = arrays
-        # successor normal edges per normal edge, per vclass mask
-        self.succ: List[List[Tuple[int, int]]] = [[] for _ in range(n_edges)]  # (to_edge, perm)
-        seen = set()
+        # successor normal edges per normal edge, per vclass mask.  The transition cost is what SUMO's router adds
+        # between two normal edges: the travel time over the internal (via) lanes plus weights.minor-penalty
+        # (1.5 s) for every unsignalised minor link on the way (MSEdge::recalcCache).
+        self.succ: List[List[Tuple[int, int, float]]] = [[] for _ in range(n_edges)]  # (to_edge, perm, via cost)
+        best: Dict[Tuple[int, int, int], float] = {}
+        lo = a["lane_link_off"]
+
+        def minor(k: int) -> bool:
+            return int(a["link_tls"][k]) < 0 and chr(int(a["link_state"][k])) in "m=Zws"
+
         for k in range(len(a["link_from"])):
             fl, tl = int(a["link_from"][k]), int(a["link_to"][k])
             if a["lane_internal"][fl]:
                 continue
             fe, te = int(a["lane_edge"][fl]), int(a["link_to_edge"][k])
             perm = int(a["lane_perm"][fl]) & int(a["lane_perm"][tl])
+            c = 1.5 if minor(k) else 0.0
+            v, hops = int(a["link_via"][k]), 0
+            while v >= 0 and hops < 8:
+                c += float(a["lane_len"][v]) / max(float(a["lane_vmax"][v]), 0.1)
+                k2 = int(lo[v])
+                if k2 >= int(lo[v + 1]):
+                    break
+                if minor(k2):
+                    c += 1.5
+                v = int(a["link_via"][k2])
+                hops += 1
             key = (fe, te, perm)
-            if key in seen:
-                continue
-            seen.add(key)
-            self.succ[fe].append((te, perm))
+            if key not in best or c < best[key]:
+                best[key] = c
+        for (fe, te, perm), c in best.items():
+            self.succ[fe].append((te, perm, c))
+        for lst in self.succ:
+            lst.sort()
         self.cost = np.zeros(n_edges, np.float64)
         for e in range(n_edges):
             l0 = int(a["edge_lane0"][e])
@@ -303,10 +324,10 @@ class Router:
             if u == dst:
                 found = True
                 break
-            for v, perm in self.succ[u]:
+            for v, perm, via in self.succ[u]:
                 if not (perm & vbit):
                     continue
-                nd = d + self.cost[v]
+                nd = d + via + self.cost[v]
                 if v not in dist or nd < dist[v] - 1e-12:
                     dist[v] = nd
                     prev[v] = u
@@ -408,7 +429,11 @@ def compile_demand(arrays: Dict[str, np.ndarray], meta: Dict[str, object], idx: 
 
     n_unroutable = 0
     rows = []
+    n_before_begin = 0
     for fi, tr in enumerate(demand.trips):
+        if tr.depart < begin:     # SUMO discards vehicles whose departure lies before --begin (cologne3: 1638)
+            n_before_begin += 1
+            continue
         vti = vt_index.get(tr.vtype, vt_index.get("DEFAULT_VEHTYPE", 0))
         vbit = int(vt_bit[vti])
         if tr.edges is not None:
@@ -456,6 +481,7 @@ def compile_demand(arrays: Dict[str, np.ndarray], meta: Dict[str, object], idx: 
         trip_vtype=np.array([r[4] for r in rows], np.int32).reshape(-1),
     )
     dmeta = dict(vtype_ids=vt_ids, n_trips_file=len(demand.trips), n_unroutable=n_unroutable,
+                 n_before_begin=n_before_begin,
                  trip_ids=[demand.trips[r[2]].id for r in rows])
     return out, dmeta
 
@@ -688,6 +714,16 @@ def compile_scenario(net: Net, demand: Optional[Demand], map_name: str, map_conf
     if "origin_lane" in arrays:
         w_off, w_lane, w_dist = compile_watch(arrays, arrays["origin_lane"].tolist())
         arrays.update(origin_watch_off=w_off, origin_watch_lane=w_lane, origin_watch_dist=w_dist)
+    # lanes a vehicle can change into: the same upstream table, so that a lane changer sees who is about to come
+    # out of the junction behind it (empty for single-lane edges and internal lanes)
+    L = len(arrays["lane_len"])
+    multi = [l for l in range(L) if not arrays["lane_internal"][l]
+             and (arrays["lane_left"][l] >= 0 or arrays["lane_right"][l] >= 0)]
+    m_off, m_lane, m_dist = compile_watch(arrays, multi)
+    lw_off = np.zeros(L + 1, np.int32)
+    for i, l in enumerate(multi):
+        lw_off[l + 1] = m_off[i + 1] - m_off[i]
+    arrays.update(lane_watch_off=np.cumsum(lw_off).astype(np.int32), lane_watch_lane=m_lane, lane_watch_dist=m_dist)
     meta.update(dict(map_name=map_name, begin=begin,
                      map_config={k: v for k, v in map_config.items() if k not in ('net', 'route')},
                      phase_pairs=signal_config.get('phase_pairs'),
