@@ -304,11 +304,12 @@ def smem_bytes(vcap: int, n_lanes: int, n_tls: int, n_signals: int, n_origins: i
     o = al(o + max(n_signals, 1) * 4)
     o = al(o + max(n_origins, 1) * 4)
     o = al(o + max(n_origins, 1) * 4)
-    o = al(o + max(n_origins, 1) * 20)
+    o = al(o + max(n_origins, 1) * 12)
     o = al(o + n_vtypes * 32)
     o = al(o + 16 * 4)
-    o = al(o + 64 * 4)
-    o = al(o + max(n_sig_lanes, 1) * 20)
+    o = al(o + 48 * 4)
+    if n_sig_lanes * 20 > vcap * 6:      # else the observe scratch shares the plan scratch
+        o = al(o + max(n_sig_lanes, 1) * 20)
     o = al(o + 16)
     o = al(o + (2 * vcap + max(n_origins, 1)) * 2)
     o = al(o + max(n_origins, 1) * 2)

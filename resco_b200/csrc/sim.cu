@@ -48,11 +48,14 @@ __host__ __device__ inline SmemLayout make_layout(const RsScenario& sc) {
   m.off_next_phase = o; o = align16(o + (size_t)(m.S > 0 ? m.S : 1) * 4);
   m.off_origin_cur = o; o = align16(o + (size_t)(m.O > 0 ? m.O : 1) * 4);
   m.off_origin_backlog = o; o = align16(o + (size_t)(m.O > 0 ? m.O : 1) * 4);
-  m.off_origin_cand = o; o = align16(o + (size_t)(m.O > 0 ? m.O : 1) * 20);
+  m.off_origin_cand = o; o = align16(o + (size_t)(m.O > 0 ? m.O : 1) * 12);
   m.off_vt = o; o = align16(o + (size_t)m.n_vt * 8 * 4);
   m.off_hdr = o; o = align16(o + (size_t)kHdrInts * 4);
-  m.off_misc = o; o = align16(o + 64 * 4);
-  m.off_obs = o; o = align16(o + (size_t)(m.SL > 0 ? m.SL : 1) * 5 * 4);
+  m.off_misc = o; o = align16(o + 48 * 4);
+  // the per-lane observation scratch is only live in observe_body: it shares the plan scratch (vn + newlane, which
+  // are contiguous) when it fits there
+  if ((size_t)m.SL * 5 * 4 <= (size_t)m.vcap * 6) m.off_obs = m.off_vn;
+  else { m.off_obs = o; o = align16(o + (size_t)(m.SL > 0 ? m.SL : 1) * 5 * 4); }
   m.off_mbar = o; o = align16(o + 16);
   m.off_dirty = o; o = align16(o + ((size_t)2 * m.vcap + (size_t)(m.O > 0 ? m.O : 1)) * 2);   // lanes touched this tick
   m.off_oklist = o; o = align16(o + (size_t)(m.O > 0 ? m.O : 1) * 2);                          // origins with a candidate
@@ -65,7 +68,7 @@ enum { M_NARR = 0, M_NOK, M_NAFTER, M_NDIRTY, M_NOKC, M_WARP = 16 /* 32 ints of 
 
 constexpr int kDirty = 0x40000000;   // flag bit in cnt2[l]: the lane gained or lost a vehicle this tick
 
-struct OriginCand { int32_t route, vt, vid, ok_dd, unsafe; };   // ok_dd: -1 not ok, else depart delay
+struct OriginCand { int32_t vid; uint16_t route; int16_t ok_dd; int32_t vt; };   // ok_dd: -1 not ok, -2 refused by capacity, else depart delay
 
 // ------------------------------------------------------------------------------------------------
 template <int BLOCK>
@@ -197,7 +200,7 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
     // so an origin with nothing due costs one shared-memory compare
     if (!sc.synthetic && !(__int_as_float(origin_backlog[o]) <= (float)T.tick)) { cand[o].ok_dd = -1; continue; }
     int lane = __ldg(sc.origin_lane + o);
-    OriginCand c; c.ok_dd = -1; c.route = 0; c.vt = 0; c.vid = 0; c.unsafe = 0;
+    OriginCand c; c.ok_dd = -1; c.route = 0; c.vt = 0; c.vid = 0;
     bool have = false;
     int dd = 0;
     if (sc.synthetic) {
@@ -824,8 +827,8 @@ static int launch_run(RsSim* s, const RunArgs& a, cudaStream_t st) {
 
 // (threads per instance, instances per CTA, min CTAs/SM for __launch_bounds__: 1 = registers uncapped,
 //  1024/(TPI*G) = 64 registers per thread)
-#define RS_VARIANTS(X) X(32, 1, 1) X(32, 1, 32) X(32, 4, 8) X(64, 1, 1) X(64, 1, 16) X(64, 2, 1) X(64, 2, 8) X(64, 4, 1) \
-  X(64, 4, 4) X(64, 6, 1) X(64, 8, 2) X(64, 8, 1) X(64, 9, 1) X(32, 16, 1) X(32, 8, 1) X(128, 4, 1) X(128, 1, 1) X(128, 1, 8) X(128, 2, 1) X(128, 2, 4) X(128, 4, 2) X(256, 1, 1) X(256, 1, 4)
+#define RS_VARIANTS(X) X(64, 1, 1) X(64, 2, 1) X(64, 4, 1) X(64, 6, 1) X(64, 8, 1) X(32, 8, 1) X(32, 16, 1) \
+  X(128, 1, 1) X(128, 2, 1) X(128, 4, 1) X(256, 1, 1)
 
 static int run(RsSim* s, const RunArgs& a, cudaStream_t st) {
 #define X(B, G, M) if (s->block == B && s->group == G && s->minb == M) return launch_run<B, G, M>(s, a, st);
