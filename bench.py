@@ -332,7 +332,7 @@ def run_ours(args):
             "config": {"workload": f"{args.map} ({sim.S} signals) / MaxPressure / {n_env} lock-step instances per GPU"
                                    + (f" / synthetic Bernoulli demand {args.synthetic_rate:g} veh/h/entry-lane" if args.synthetic_rate > 0 else ""),
                        "n_env_per_gpu": n_env, "n_env_total": total_env, "sim_ticks_per_env_step": m.struct.step_length,
-                       "vcap": m.struct.vcap, "threads_per_instance": int(os.environ.get("RESCO_B200_BLOCK", "64")), "instances_per_cta": int(os.environ.get("RESCO_B200_GROUP", "8")), "persistent_grid": os.environ.get("RESCO_B200_PERSIST", "1") != "0",
+                       "vcap": m.struct.vcap, **sim.launch_shape(), "persistent_grid": os.environ.get("RESCO_B200_PERSIST", "1") != "0",
                        "l2": "flushed between timed steps (256 MiB memset, untimed)",
                        "timing": "per-step CUDA events on the launching stream, summed; max over ranks",
                        "allgather_obs": bool(gather_buf is not None),

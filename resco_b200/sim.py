@@ -39,7 +39,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
 EXPORTS = ["rs_last_error", "rs_abi_version", "rs_create", "rs_destroy", "rs_reset", "rs_set_phase", "rs_tick",
            "rs_observe", "rs_env_step", "rs_env_step_host", "rs_env_step_host_async", "rs_wait", "rs_policy_maxpressure", "rs_get_obs", "rs_get_stats",
-           "rs_dump_vehicles", "rs_get_phases", "rs_get_trip_records", "rs_kernel_launches", "rs_last_step_ms"]
+           "rs_dump_vehicles", "rs_get_phases", "rs_get_trip_records", "rs_kernel_launches", "rs_last_step_ms", "rs_get_launch_shape"]
 
 
 def load_library():
@@ -73,6 +73,7 @@ def load_library():
     lib.rs_kernel_launches.restype = C.c_int64
     lib.rs_kernel_launches.argtypes = [C.c_void_p]
     lib.rs_last_step_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    lib.rs_get_launch_shape.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 4
     _LIB = lib
     return lib
 
@@ -270,6 +271,12 @@ class VecSim:
 
     def kernel_launches(self) -> int:
         return int(self.lib.rs_kernel_launches(self._h))
+
+    def launch_shape(self) -> dict:
+        v = [C.c_int32(0) for _ in range(4)]
+        _check(self.lib, self.lib.rs_get_launch_shape(self._h, *[C.byref(x) for x in v]))
+        return dict(threads_per_instance=v[0].value, instances_per_cta=v[1].value, grid_ctas=v[2].value,
+                    smem_bytes_per_cta=v[3].value)
 
     def last_step_ms(self) -> float:
         ms = C.c_float(0)
