@@ -63,6 +63,20 @@ __host__ __device__ inline SmemLayout make_layout(const RsScenario& sc) {
   return m;
 }
 
+// Optional per-phase cycle accounting (build with -DRS_PHASE_CLOCKS=1, tools/phase_clocks.sh): thread 0 of the CTA
+// charges the cycles since the previous mark to slot i; k_run adds the CTA totals to DevSim::phase_clocks.
+#ifndef RS_PHASE_CLOCKS
+#define RS_PHASE_CLOCKS 0
+#endif
+#if RS_PHASE_CLOCKS
+__shared__ long long s_pclk[24];
+__shared__ long long s_pclk_last;
+#define PCLK(i) do { if (threadIdx.x == 0) { long long c_ = clock64(); s_pclk[i] += c_ - s_pclk_last; s_pclk_last = c_; } } while (0)
+#else
+#define PCLK(i) do { } while (0)
+#endif
+enum { PC_STAGE = 0, PC_S0, PC_S1, PC_S2, PC_S3A, PC_S3B, PC_S4, PC_S5, PC_S6, PC_S7, PC_OBS, PC_WRITE, PC_SCHED, PC_N };
+
 // misc slots
 enum { M_NARR = 0, M_NOK, M_NAFTER, M_NDIRTY, M_NOKC, M_WARP = 16 /* 32 ints of warp totals */ };
 
@@ -107,6 +121,7 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
   }
   if (tid == 0) { misc[M_NARR] = 0; misc[M_NOK] = 0; misc[M_NDIRTY] = 0; misc[M_NOKC] = 0; }
   __syncthreads();
+  PCLK(PC_S0);
 
   // a lane that gains or loses a vehicle is put on the dirty list once (flag bit in its counter)
   auto mark_dirty = [&](int l) {
@@ -121,6 +136,7 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
     vn[i] = v; newlane[i] = (uint16_t)tg;
   }
   __syncthreads();
+  PCLK(PC_S1);
 
   // ---- S2: move: update in place, hand-off across lanes, bucket movers by target lane ----
   for (int i = tid; i < n; i += BLOCK) {
@@ -178,6 +194,7 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
     }
   }
   __syncthreads();
+  PCLK(PC_S2);
 
   // ---- S3a: arrivals (deterministic CSR order) and insertion candidates ----
   if (tid == 0) {
@@ -279,6 +296,7 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
     cand[o] = c;
   }
   __syncthreads();
+  PCLK(PC_S3A);
 
   // ---- S3b: capacity resolution (origin order) ----
   const int nokc = misc[M_NOKC];
@@ -309,9 +327,11 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
     }
   }
   __syncthreads();
+  PCLK(PC_S3B);
 
   // ---- S4: new lane offsets ----
   block_prefix<BLOCK>(cnt2, start2, L, misc + M_WARP);   // counts are read without the dirty flag bit
+  PCLK(PC_S4);
 
   // ---- S5: per-lane merge: stayers keep their order, movers merge in by position ----
   const int ndirty = misc[M_NDIRTY];
@@ -341,6 +361,7 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
     while (mv >= 0) { newidx[mv] = (uint16_t)w++; mv = next_mover(T.pos[mv], mv); }
   }
   __syncthreads();
+  PCLK(PC_S5);
 
   // ---- S6: scatter into the other buffer; newcomers at the back of their origin lane ----
   {
@@ -369,6 +390,7 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
     }
   }
   __syncthreads();
+  PCLK(PC_S6);
 
   // ---- S7: swap, bookkeeping ----
   {
@@ -394,6 +416,7 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
     T.tick += 1;
   }
   __syncthreads();
+  PCLK(PC_S7);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -592,6 +615,7 @@ __device__ __forceinline__ void run_instance(const DevSim& D, const RunArgs& A, 
     __syncthreads();
   }
   const int n_ticks = A.ticks_a + A.ticks_b;
+  PCLK(PC_STAGE);
 #pragma unroll 1
   for (int k = 0; k <= n_ticks; ++k) {
     if (k == A.ticks_a && A.do_set) {   // Signal.set_phase after the yellow interval
@@ -602,6 +626,7 @@ __device__ __forceinline__ void run_instance(const DevSim& D, const RunArgs& A, 
     tick_body<BLOCK>(D, m, smem, T, cur, oth, start2, env);
   }
   if (A.do_observe) observe_body<BLOCK>(D, m, smem, T, env);
+  PCLK(PC_OBS);
 
   // ---- write the tile back ----
   {
@@ -634,6 +659,7 @@ __device__ __forceinline__ void run_instance(const DevSim& D, const RunArgs& A, 
     D.origin_cur[(size_t)env * m.O + i] = origin_cur[i];
     if (sc.synthetic) D.origin_backlog[(size_t)env * m.O + i] = origin_backlog[i];
   }
+  PCLK(PC_WRITE);
 }
 
 // Persistent launch: the grid holds as many CTAs as are resident at once (148 SMs x CTAs/SM); each CTA
@@ -647,6 +673,9 @@ __global__ void __launch_bounds__(TPI * G, MINB) k_run(const __grid_constant__ D
   unsigned char* my = smem + (size_t)(threadIdx.x / TPI) * m.total;
   __shared__ int s_env;
   uint32_t tma_parity = 0;
+#if RS_PHASE_CLOCKS
+  if (threadIdx.x == 0) { for (int i = 0; i < 24; ++i) s_pclk[i] = 0; s_pclk_last = clock64(); }
+#endif
   if (D.use_tma) {
     if (threadIdx.x % TPI == 0) mbar_init((uint64_t*)(my + m.off_mbar), 1);
     __syncthreads();
@@ -657,6 +686,7 @@ __global__ void __launch_bounds__(TPI * G, MINB) k_run(const __grid_constant__ D
       if (threadIdx.x == 0) s_env = atomicAdd(D.work_counter, G);
       __syncthreads();
     }
+    PCLK(PC_SCHED);
     const int env0 = D.persistent ? s_env : (int)blockIdx.x * G;
     if (env0 >= D.n_env) break;
     // a slot past the end of the batch repeats the last instance (same inputs -> identical stores)
@@ -664,6 +694,10 @@ __global__ void __launch_bounds__(TPI * G, MINB) k_run(const __grid_constant__ D
     if (!D.persistent) break;
     __syncthreads();
   }
+#if RS_PHASE_CLOCKS
+  if (threadIdx.x == 0 && D.phase_clocks)
+    for (int i = 0; i < PC_N; ++i) atomicAdd(D.phase_clocks + i, (unsigned long long)s_pclk[i]);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -950,6 +984,7 @@ extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, ui
   s->d.use_tma = et ? atoi(et) : 1;
   s->n_sm = prop.multiProcessorCount;
   TRY(dev_alloc(s, s->d.work_counter, 1));
+  TRY(dev_alloc(s, s->d.phase_clocks, 24));
   const char* ec = getenv("RESCO_B200_CARVEOUT");
   s->carveout = ec ? atoi(ec) : -1;
   TRY(configure(s));
@@ -1168,6 +1203,16 @@ extern "C" int rs_get_trip_records(RsSim* s, int32_t env, int32_t* h_arrival_tic
 }
 
 extern "C" int64_t rs_kernel_launches(RsSim* s) { return s ? s->launches : 0; }
+
+// Diagnostics: cycles per kernel phase summed over CTAs since rs_create (all zero unless the library was built with
+// -DRS_PHASE_CLOCKS=1; see tools/phase_clocks.sh).  Not part of include/resco_b200.h.
+extern "C" int rs_debug_phase_clocks(RsSim* s, unsigned long long* h_out24) {
+  if (!s || !h_out24) return fail(RS_ERR_INVALID, "rs_debug_phase_clocks: bad arguments");
+  CK(cudaSetDevice(s->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(h_out24, s->d.phase_clocks, 24 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return RS_PHASE_CLOCKS;
+}
 
 extern "C" int rs_get_launch_shape(RsSim* s, int32_t* threads_per_instance, int32_t* instances_per_cta, int32_t* grid_ctas,
                                    int32_t* smem_bytes_per_cta) {

@@ -64,6 +64,7 @@ struct DevSim {
   int32_t *sig_queue_len, *sig_max_queue;
   int4* trip_rec;         // [N][n_trips] {arrival tick, depart tick, timeLoss bits, depart delay} or null
   int32_t* work_counter;  // dynamic instance scheduler of the persistent launch
+  unsigned long long* phase_clocks;   // [24] diagnostics (RS_PHASE_CLOCKS builds)
   int32_t persistent;
   int32_t use_tma;        // stage the tile with cp.async.bulk (TMA 1-D bulk copies) instead of LDG/STG
 };
