@@ -88,7 +88,7 @@ struct OriginCand { int32_t vid; uint16_t route; int16_t ok_dd; int32_t vt; };  
 template <int BLOCK>
 __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, unsigned char* smem, Tile& T, uint32_t*& cur,
                           uint32_t*& oth, uint16_t*& start2, const int env) {
-  const RsScenario& sc = D.sc;
+  const DevScenario& sc = D.sc;
   const int tid = threadIdx.x % BLOCK;   // BLOCK = threads per instance (a CTA may hold several instances)
   const int L = m.L;
   float* vn = (float*)(smem + m.off_vn);
@@ -143,7 +143,7 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
     int l = v_lane(T, i);
     int vt = v_vtype(T, i);
     float v1 = vn[i];
-    float vmaxl = fminf(__ldg(sc.lane_vmax + l) * T.sf[i], VTT(T, vt, VT_VMAX));
+    float vmaxl = fminf(__ldg(&sc.lane_rec[l].vmax) * T.sf[i], VTT(T, vt, VT_VMAX));
     T.speed[i] = v1;
     uint32_t w = T.wr[i];
     uint32_t wait = v1 < kHaltSpeed ? (w & 0xFFFFu) + 1u : 0u;
@@ -158,14 +158,13 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
     if (tg != l) { curl = tg; lcc = kLcCooldown; }
     else {
       int guard = 0;
-      while (p > __ldg(sc.lane_len + curl) && guard++ < 64) {
+      while (p > __ldg(&sc.lane_rec[curl].len) && guard++ < 64) {
         int k = guard == 1 ? v_nextlink(sc, T, i, l) : next_link(sc, curl, route, cc);
         if (k == -1) { curl = -1; break; }
-        if (k == -2) { p = __ldg(sc.lane_len + curl); break; }
-        p -= __ldg(sc.lane_len + curl);
-        int via = __ldg(sc.link_via + k);
-        curl = via >= 0 ? via : __ldg(sc.link_to + k);
-        if (!__ldg(sc.lane_internal + curl)) cc += 1;
+        if (k == -2) { p = __ldg(&sc.lane_rec[curl].len); break; }
+        p -= __ldg(&sc.lane_rec[curl].len);
+        curl = __ldg(&sc.link_rec[k].nxt);
+        if (!__ldg(&sc.lane_rec[curl].internal)) cc += 1;
       }
     }
     T.pos[i] = p;
@@ -245,7 +244,7 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
     }
     if (have) {
       float len = VTT(T, c.vt, VT_LEN), mingap = VTT(T, c.vt, VT_GAP);
-      bool ok = len <= __ldg(sc.lane_len + lane);
+      bool ok = len <= __ldg(&sc.lane_rec[lane].len);
       if (ok) {
         // post-move tail of the origin lane = last element of the merged (stayers + movers) order
         int a = T.lane_start[lane], b = T.lane_start[lane + 1];
@@ -276,17 +275,16 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
       if (h < 0) continue;
       // cheap test first: only a head that could not brake in time is worth the route look-ahead
       int hvt = v_vtype(T, h);
-      float gap = (__ldg(sc.lane_len + pl) - T.pos[h]) + __ldg(sc.origin_watch_dist + w) - VTT(T, hvt, VT_GAP);
+      float gap = (__ldg(&sc.lane_rec[pl].len) - T.pos[h]) + __ldg(sc.origin_watch_dist + w) - VTT(T, hvt, VT_GAP);
       if (!(gap < brake_gap(T.speed[h], VTT(T, hvt, VT_DECEL), VTT(T, hvt, VT_TAU)))) continue;
       int cur = pl, cc = v_cursor(T, h), hr = v_route(T, h);
       bool reaches = false;
       for (int hop = 0; hop < 4; ++hop) {
         int k = hop == 0 ? v_nextlink(sc, T, h, pl) : next_link(sc, cur, hr, cc);
         if (k < 0) break;
-        int via = __ldg(sc.link_via + k);
-        int nxt = via >= 0 ? via : __ldg(sc.link_to + k);
+        int nxt = __ldg(&sc.link_rec[k].nxt);
         if (nxt == lane) { reaches = true; break; }
-        if (!__ldg(sc.lane_internal + nxt)) cc += 1;
+        if (!__ldg(&sc.lane_rec[nxt].internal)) cc += 1;
         cur = nxt;
       }
       if (reaches) ok = false;
@@ -423,7 +421,7 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
 // Signal.observe (traffic_signal.py:189-235) + states.mplight / wave + rewards.* + calc_metrics
 template <int BLOCK>
 __device__ __forceinline__ void observe_body(const DevSim& D, const SmemLayout& m, unsigned char* smem, Tile& T, int env) {
-  const RsScenario& sc = D.sc;
+  const DevScenario& sc = D.sc;
   const int tid = threadIdx.x % BLOCK, lane_id = tid & 31, wid = tid >> 5, nw = BLOCK / 32;
   int32_t* hdr = (int32_t*)(smem + m.off_hdr);
   float* ob = (float*)(smem + m.off_obs);   // [5][SL]
@@ -432,8 +430,8 @@ __device__ __forceinline__ void observe_body(const DevSim& D, const SmemLayout& 
   const uint32_t eprev = (uint32_t)(e - 1) & 0xFFFFu;
   for (int q = wid; q < SL; q += nw) {     // one warp per inbound lane: segmented shuffle reduction
     int lane = __ldg(sc.sig_lane + q);
-    int sg = __ldg(sc.lane_sig + lane);
-    float tdist = __ldg(sc.lane_tls_dist + lane), llen = __ldg(sc.lane_len + lane);
+    int sg = __ldg(&sc.lane_rec[lane].sig);
+    float tdist = __ldg(&sc.lane_rec[lane].tls_dist), llen = __ldg(&sc.lane_rec[lane].len);
     float queue = 0, appr = 0, tw = 0, mw = 0, ss = 0;
     int a = T.lane_start[lane], b = T.lane_start[lane + 1];
     for (int i = a + lane_id; i < b; i += 32) {
@@ -505,7 +503,7 @@ __device__ __forceinline__ void observe_body(const DevSim& D, const SmemLayout& 
 }
 
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void dev_set_phase(const RsScenario& sc, Tile& T, int sg, int idx) {
+__device__ __forceinline__ void dev_set_phase(const DevScenario& sc, Tile& T, int sg, int idx) {
   int t = __ldg(sc.sig_tls + sg);
   int p0 = __ldg(sc.tls_phase_off + t), np = __ldg(sc.tls_phase_off + t + 1) - p0;
   if (idx < 0 || idx >= np) return;
@@ -517,7 +515,7 @@ __device__ __forceinline__ void dev_set_phase(const RsScenario& sc, Tile& T, int
 template <int BLOCK>
 __device__ __forceinline__ void run_instance(const DevSim& D, const RunArgs& A, const SmemLayout& m,
                                              unsigned char* smem, const int env, uint32_t& tma_parity) {
-  const RsScenario& sc = D.sc;
+  const DevScenario& sc = D.sc;
   const int tid = threadIdx.x % BLOCK;
   uint32_t* cur = (uint32_t*)(smem + m.off_bufA);
   uint32_t* oth = (uint32_t*)(smem + m.off_bufB);
@@ -703,7 +701,7 @@ __global__ void __launch_bounds__(TPI * G, MINB) k_run(const __grid_constant__ D
 // ------------------------------------------------------------------------------------------------
 __global__ void k_reset(DevSim D) {
   const int env = blockIdx.x;
-  const RsScenario& sc = D.sc;
+  const DevScenario& sc = D.sc;
   for (int i = threadIdx.x; i < kHdrInts; i += blockDim.x) D.hdr[(size_t)env * kHdrInts + i] = 0;
   for (int i = threadIdx.x; i < sc.n_tls; i += blockDim.x) {
     D.tls_phase[(size_t)env * sc.n_tls + i] = sc.tls_init_phase[i];
@@ -719,7 +717,7 @@ __global__ void k_reset(DevSim D) {
 }
 
 __global__ void k_set_phase(DevSim D, const int32_t* phase, const uint8_t* mask) {
-  const RsScenario& sc = D.sc;
+  const DevScenario& sc = D.sc;
   int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= D.n_env * sc.n_signals) return;
   if (mask && !mask[x]) return;
@@ -736,7 +734,7 @@ __global__ void k_set_phase(DevSim D, const int32_t* phase, const uint8_t* mask)
 __global__ void k_stats(DevSim D, RsStats* out) {
   int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= D.n_env) return;
-  const RsScenario& sc = D.sc;
+  const DevScenario& sc = D.sc;
   const int32_t* h = D.hdr + (size_t)env * kHdrInts;
   RsStats st;
   st.tick = h[H_TICK]; st.n_active = h[H_NVEH]; st.n_inserted = h[H_NINS]; st.n_arrived = h[H_NARR];
@@ -771,7 +769,7 @@ __global__ void k_stats(DevSim D, RsStats* out) {
 // order: [S][n_pairs][2] = (pair index, action) in evaluation order, pair index -1 terminates.
 __global__ void k_policy(DevSim D, const int32_t* pairs, int n_pairs, const int32_t* order, int use_wave,
                          int32_t* actions) {
-  const RsScenario& sc = D.sc;
+  const DevScenario& sc = D.sc;
   int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= D.n_env * sc.n_signals) return;
   int sg = x % sc.n_signals;
@@ -902,9 +900,75 @@ extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, ui
   RsSim* s = new RsSim();
   s->device = device; s->launches = 0; s->timed = false; s->n_pairs_alloc = 0;
   s->pending = false; s->pend_obs = nullptr; s->pend_rew = nullptr; s->ev_done = nullptr;
-  s->d.sc = *sc; s->d.n_env = n_env; s->d.seed = seed; s->d.first_env_id = 0;
-  RsScenario& d = s->d.sc;
+  static_cast<RsScenario&>(s->d.sc) = *sc; s->d.n_env = n_env; s->d.seed = seed; s->d.first_env_id = 0;
+  DevScenario& d = s->d.sc;
   const int L = sc->n_lanes, K = sc->n_links, S = sc->n_signals;
+  {   // packed device tables (LaneRec / LinkRec / FoeRec / route_step_link), built from the caller's host arrays
+    std::vector<LaneRec> lr((size_t)L + 1);
+    std::vector<LinkRec> kr((size_t)K + 1);
+    std::vector<FoeRec> fr((size_t)sc->n_foes + 1);
+    std::vector<uint8_t> rsl((size_t)(sc->n_route_steps > 0 ? sc->n_route_steps : 1) * 8, 0xFDu);
+    memset(lr.data(), 0, lr.size() * sizeof(LaneRec)); memset(kr.data(), 0, kr.size() * sizeof(LinkRec));
+    memset(fr.data(), 0, fr.size() * sizeof(FoeRec));
+    for (int l = 0; l <= L; ++l) {
+      LaneRec& r = lr[l];
+      r.link_off = sc->lane_link_off[l];
+      if (l == L) break;
+      r.len = sc->lane_len[l]; r.vmax = sc->lane_vmax[l]; r.internal = sc->lane_internal[l];
+      r.index = sc->lane_index[l]; r.left = sc->lane_left[l]; r.right = sc->lane_right[l]; r.perm = sc->lane_perm[l];
+      r.tls_dist = sc->lane_tls_dist[l]; r.sig = sc->lane_sig[l]; r.sig_slot = sc->lane_sig_slot[l];
+    }
+    for (int k = 0; k <= K; ++k) {
+      LinkRec& r = kr[k];
+      r.foe_off = sc->link_foe_off[k];
+      if (k == K) break;
+      r.from = sc->link_from[k]; r.to = sc->link_to[k]; r.via = sc->link_via[k]; r.to_edge = sc->link_to_edge[k];
+      r.tls = sc->link_tls[k]; r.tlidx = sc->link_tlidx[k]; r.state = sc->link_state[k]; r.cont = sc->link_cont[k];
+      r.via_len = sc->link_via_len[k]; r.last_int = sc->link_last_int[k]; r.parent = sc->link_parent[k];
+      r.nxt = r.via >= 0 ? r.via : r.to;
+    }
+    for (int i = 0; i < sc->n_foes; ++i) {
+      FoeRec& r = fr[i];
+      const int f = sc->foe_link[i];
+      r.link = f; r.flags = (sc->foe_flags[i] & 7) | (sc->link_cont[f] ? 8 : 0);
+      r.last_int = sc->link_last_int[f]; r.from = sc->link_from[f];
+      r.slot = sc->link_cont[f] ? sc->link_via[f] : -1; r.via_len = sc->link_via_len[f];
+      r.len_from = sc->lane_len[r.from]; r.len_slot = r.slot >= 0 ? sc->lane_len[r.slot] : 0.0f;
+    }
+    fr[sc->n_foes].last_int = -1; fr[sc->n_foes].slot = -1;
+    // choose_link tabulated per (route step, lane index): prefer a target lane that is "best", then "ok", then any
+    for (int r = 0; r < sc->n_routes; ++r) {
+      const int ro = sc->route_off[r], rn = sc->route_off[r + 1] - ro;
+      for (int c = 0; c < rn; ++c) {
+        const int e = sc->route_edge[ro + c];
+        for (int j = 0; j < sc->edge_nlanes[e] && j < 8; ++j) {
+          const int lane = sc->edge_lane0[e] + j;
+          if (sc->lane_index[lane] != j || sc->lane_internal[lane]) {
+            rs_destroy(s);
+            return fail(RS_ERR_INVALID, "rs_create: lanes of a route edge are not contiguous by index");
+          }
+          int code;
+          if (c + 1 >= rn) code = 0xFE;
+          else {
+            const int ne = sc->route_edge[ro + c + 1], mask = sc->route_mask[ro + c + 1];
+            int best = -2, rank = 0;
+            for (int k = sc->lane_link_off[lane]; k < sc->lane_link_off[lane + 1]; ++k) {
+              if (sc->link_to_edge[k] != ne) continue;
+              const int ti = sc->lane_index[sc->link_to[k]];
+              const int q = ((mask >> (8 + ti)) & 1) ? 3 : (((mask >> ti) & 1) ? 2 : 1);
+              if (q > rank) { rank = q; best = k; }
+            }
+            code = best < 0 ? 0xFD : best - sc->lane_link_off[lane];
+            if (best >= 0 && code >= 0xFD) { rs_destroy(s); return fail(RS_ERR_INVALID, "rs_create: more than 252 links on one lane"); }
+          }
+          rsl[(size_t)(ro + c) * 8 + j] = (uint8_t)code;
+        }
+      }
+    }
+    const LaneRec* lp = lr.data(); const LinkRec* kp = kr.data(); const FoeRec* fp = fr.data(); const uint8_t* rp = rsl.data();
+    TRY(dev_dup(s, lp, lr.size())); TRY(dev_dup(s, kp, kr.size())); TRY(dev_dup(s, fp, fr.size())); TRY(dev_dup(s, rp, rsl.size()));
+    d.lane_rec = lp; d.link_rec = kp; d.foe_rec = fp; d.route_step_link = rp;
+  }
   TRY(dev_dup(s, d.lane_len, L)); TRY(dev_dup(s, d.lane_vmax, L)); TRY(dev_dup(s, d.lane_edge, L));
   TRY(dev_dup(s, d.lane_index, L)); TRY(dev_dup(s, d.lane_perm, L)); TRY(dev_dup(s, d.lane_internal, L));
   TRY(dev_dup(s, d.lane_left, L)); TRY(dev_dup(s, d.lane_right, L)); TRY(dev_dup(s, d.lane_link_off, L + 1));
@@ -1042,7 +1106,7 @@ extern "C" int rs_observe(RsSim* s, void* stream) {
 
 extern "C" int rs_env_step(RsSim* s, const int32_t* d_actions, void* stream) {
   if (!s || !d_actions) return fail(RS_ERR_INVALID, "rs_env_step: bad arguments");
-  const RsScenario& sc = s->d.sc;
+  const DevScenario& sc = s->d.sc;
   RunArgs a{d_actions, 1, sc.yellow_length, 1, sc.step_length - sc.yellow_length, 1};
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaEventRecord(s->ev0, st));

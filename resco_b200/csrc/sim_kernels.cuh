@@ -43,9 +43,37 @@ enum { H_TICK = 0, H_NVEH, H_EPOCH, H_NINS, H_NARR, H_ANOM, H_ACTIVE, H_F_DELAY_
 // vtype table columns
 enum { VT_LEN = 0, VT_GAP, VT_ACCEL, VT_DECEL, VT_TAU, VT_SIGMA, VT_VMAX, VT_DEV };
 
-// Device copy of RsScenario (device pointers) + per-sim buffers.
+// Device-side network tables.  rs_create packs the flat per-field arrays of RsScenario (the ABI) into one record per
+// lane / link / foe, so that everything the junction logic needs about one object sits in one or two 32-byte sectors
+// (one L1 miss instead of a dozen) and the dependent load chains of the right-of-way loops are one level deep.
+struct alignas(16) LaneRec {
+  float len, vmax; int32_t link_off, internal;
+  int32_t index, left, right, perm;
+  float tls_dist; int32_t sig, sig_slot, pad;
+};                                                   // 48 B; [n_lanes + 1] (sentinel carries link_off = n_links)
+struct alignas(16) LinkRec {
+  int32_t from, to, via, to_edge;
+  int32_t tls, tlidx, state, cont;
+  float via_len; int32_t last_int, parent, foe_off;
+  int32_t nxt /* via >= 0 ? via : to */, pad0, pad1, pad2;
+};                                                   // 64 B; [n_links + 1] (sentinel carries foe_off = n_foes)
+struct alignas(16) FoeRec {                          // one foe of a link, joined with what link_blocked reads of it
+  int32_t link, flags, last_int, from;               // foe link f, foe_flags, link_last_int[f], link_from[f]
+  int32_t slot /* link_cont[f] ? link_via[f] : -1 */; float via_len, len_from, len_slot;
+};                                                   // 32 B; [n_foes + 1] (one readable record past the end)
+
+struct DevScenario : RsScenario {                    // base-class pointers are DEVICE pointers
+  const LaneRec* lane_rec;
+  const LinkRec* link_rec;
+  const FoeRec* foe_rec;
+  // choose_link() tabulated: [n_route_steps][8] = encode_nextlink code of the link a vehicle at route step s takes
+  // from lane index j of that step's edge (0xFE route ends, 0xFD the lane does not lead on)
+  const uint8_t* route_step_link;
+};
+
+// Device copy of the scenario + per-sim buffers.
 struct DevSim {
-  RsScenario sc;          // pointers are DEVICE pointers
+  DevScenario sc;
   int32_t n_env;
   uint64_t seed;
   int64_t first_env_id;
@@ -167,12 +195,12 @@ __device__ __forceinline__ int v_lane(const Tile& t, int i) { return (int)(t.dl[
 // cached choose_link() of the vehicle's CURRENT lane (meta bits 24..31: index relative to the lane's
 // first link, 0xFE = route ends here (-1), 0xFD = lane does not lead on (-2)); refreshed whenever the
 // vehicle enters a lane, so that the plan phase and the foe checks read it with one LDS.
-__device__ __forceinline__ uint32_t encode_nextlink(const RsScenario& sc, int lane, int k) {
-  return k == -1 ? 0xFEu : (k < 0 ? 0xFDu : (uint32_t)(k - __ldg(sc.lane_link_off + lane)));
+__device__ __forceinline__ uint32_t encode_nextlink(const DevScenario& sc, int lane, int k) {
+  return k == -1 ? 0xFEu : (k < 0 ? 0xFDu : (uint32_t)(k - __ldg(&sc.lane_rec[lane].link_off)));
 }
-__device__ __forceinline__ int v_nextlink(const RsScenario& sc, const Tile& t, int i, int lane) {
+__device__ __forceinline__ int v_nextlink(const DevScenario& sc, const Tile& t, int i, int lane) {
   uint32_t r = t.meta[i] >> 24;
-  return r == 0xFEu ? -1 : (r == 0xFDu ? -2 : __ldg(sc.lane_link_off + lane) + (int)r);
+  return r == 0xFEu ? -1 : (r == 0xFDu ? -2 : __ldg(&sc.lane_rec[lane].link_off) + (int)r);
 }
 __device__ __forceinline__ int lane_count(const Tile& t, int l) { return (int)t.lane_start[l + 1] - (int)t.lane_start[l]; }
 
@@ -193,37 +221,24 @@ __device__ __forceinline__ float speed_factor(const Tile& t, int32_t vid, float 
   return fminf(fmaxf(sf, 0.2f), 2.0f);
 }
 
-// which link does a vehicle with (route, cursor) take at the end of `lane`?  -1: route ends, -2: wrong lane
-__device__ __noinline__ int choose_link(const RsScenario& sc, int lane, int route, int cursor) {
-  int k0 = __ldg(sc.lane_link_off + lane), k1 = __ldg(sc.lane_link_off + lane + 1);
-  if (__ldg(sc.lane_internal + lane)) return k0 < k1 ? k0 : -2;
-  int ro = __ldg(sc.route_off + route), rn = __ldg(sc.route_off + route + 1) - ro;
-  if (cursor + 1 >= rn) return -1;
-  int ne = __ldg(sc.route_edge + ro + cursor + 1), mask = __ldg(sc.route_mask + ro + cursor + 1);
-  int best = -2, rank = 0;
-  for (int k = k0; k < k1; ++k) {
-    if (__ldg(sc.link_to_edge + k) != ne) continue;
-    int ti = __ldg(sc.lane_index + __ldg(sc.link_to + k));
-    int r = ((mask >> (8 + ti)) & 1) ? 3 : (((mask >> ti) & 1) ? 2 : 1);
-    if (r > rank) { rank = r; best = k; }
-  }
-  return best;
+// which link does a vehicle with (route, cursor) take at the end of `lane`?  -1: route ends, -2: wrong lane.
+// The rule (prefer a target lane that is "best", then "ok", then any; first maximum) is tabulated per route step
+// and lane index by rs_create (host_choose_link in sim.cu), so this is two dependent loads instead of a loop.
+__device__ __forceinline__ int choose_link(const DevScenario& sc, int lane, int route, int cursor) {
+  const int k0 = __ldg(&sc.lane_rec[lane].link_off);
+  if (__ldg(&sc.lane_rec[lane].internal)) return k0 < __ldg(&sc.lane_rec[lane + 1].link_off) ? k0 : -2;
+  const uint32_t r = __ldg(sc.route_step_link + (size_t)(__ldg(sc.route_off + route) + cursor) * 8 + __ldg(&sc.lane_rec[lane].index));
+  return r == 0xFEu ? -1 : (r == 0xFDu ? -2 : k0 + (int)r);
 }
-
-// choose_link with the internal-lane case (exactly one way on) resolved inline, without the call
-__device__ __forceinline__ int next_link(const RsScenario& sc, int lane, int route, int cursor) {
-  if (__ldg(sc.lane_internal + lane)) {
-    int k0 = __ldg(sc.lane_link_off + lane);
-    return k0 < __ldg(sc.lane_link_off + lane + 1) ? k0 : -2;
-  }
+__device__ __forceinline__ int next_link(const DevScenario& sc, int lane, int route, int cursor) {
   return choose_link(sc, lane, route, cursor);
 }
 
-__device__ __forceinline__ int state_now(const RsScenario& sc, const Tile& t, int k) {
-  int tl = __ldg(sc.link_tls + k);
-  if (tl < 0) return __ldg(sc.link_state + k);
+__device__ __forceinline__ int state_now(const DevScenario& sc, const Tile& t, int k) {
+  int tl = __ldg(&sc.link_rec[k].tls);
+  if (tl < 0) return __ldg(&sc.link_rec[k].state);
   // tls_state[tl] = offset of the current phase's state string (refreshed in shared memory whenever a phase changes)
-  return (int)__ldg(sc.state_chars + t.tls_state[tl] + __ldg(sc.link_tlidx + k));
+  return (int)__ldg(sc.state_chars + t.tls_state[tl] + __ldg(&sc.link_rec[k].tlidx));
 }
 
 __device__ __forceinline__ bool time_conflict(float seen, float v, float cross, float dist_f, float v_f, float cross_f) {
@@ -234,38 +249,41 @@ __device__ __forceinline__ bool time_conflict(float seen, float v, float cross, 
 }
 
 // right-of-way: must the vehicle on entry link k wait for one of its foes?
-RS_HEAVY bool link_blocked(const RsScenario& sc, const Tile& t, int k, float seen, float v, float cross) {
-  int f0 = __ldg(sc.link_foe_off + k), f1 = __ldg(sc.link_foe_off + k + 1);
+RS_HEAVY bool link_blocked(const DevScenario& sc, const Tile& t, int k, float seen, float v, float cross) {
+  const int f0 = __ldg(&sc.link_rec[k].foe_off), f1 = __ldg(&sc.link_rec[k + 1].foe_off);
+  if (f0 >= f1) return false;
+  const int4* rec = reinterpret_cast<const int4*>(sc.foe_rec);
+  int4 a = __ldg(rec + 2 * f0);                          // {link, flags, last_int, from}
   for (int fi = f0; fi < f1; ++fi) {
-    int f = __ldg(sc.foe_link + fi), fl = __ldg(sc.foe_flags + fi);
-    int li = __ldg(sc.link_last_int + f);
+    const int4 c = a;
+    a = __ldg(rec + 2 * (fi + 1));                       // next foe's record is in flight while this one is tested
+    const int f = c.x, fl = c.y, li = c.z, a0 = c.w;
     if (li >= 0 && lane_count(t, li) > 0) return true;   // somebody is crossing my path
     if (!(fl & 1)) continue;                             // I have right of way over f
-    int a0 = __ldg(sc.link_from + f);
-    if (lane_count(t, a0) > 0) {
+    const bool occ0 = lane_count(t, a0) > 0;
+    if (!occ0 && !(fl & 8)) continue;                    // bit 3: f has a waiting slot inside the junction
+    const int4 d = __ldg(rec + 2 * fi + 1);              // {slot, via_len, len_from, len_slot}
+    const float via_len = __int_as_float(d.y);
+    if (occ0) {
       int h = t.lane_start[a0];
       if (v_nextlink(sc, t, h, a0) == f) {
-        float dist_f = __ldg(sc.lane_len + a0) - t.pos[h];
+        float dist_f = __int_as_float(d.z) - t.pos[h];
         int fst = state_now(sc, t, f);
         bool goes = true;
         int hv = v_vtype(t, h);
         if (fst == 'r' || fst == 'u' || fst == 's') goes = false;
         else if (fst == 'y' && dist_f >= brake_gap(t.speed[h], VTT(t, hv, VT_DECEL), 0.0f)) goes = false;
         if (t.speed[h] < kHaltSpeed) goes = false;       // a standing foe is not approaching
-        if (goes && time_conflict(seen, v, cross, dist_f, t.speed[h],
-                                  __ldg(sc.link_via_len + f) + VTT(t, hv, VT_LEN))) return true;
+        if (goes && time_conflict(seen, v, cross, dist_f, t.speed[h], via_len + VTT(t, hv, VT_LEN))) return true;
       }
     }
-    if (__ldg(sc.link_cont + f)) {
-      int a1 = __ldg(sc.link_via + f);
-      if (lane_count(t, a1) > 0) {
-        int h = t.lane_start[a1];
-        float dist_f = __ldg(sc.lane_len + a1) - t.pos[h];
-        if (t.speed[h] >= kHaltSpeed &&
-            time_conflict(seen, v, cross, dist_f, t.speed[h],
-                          __ldg(sc.link_via_len + f) - __ldg(sc.lane_len + a1) + VTT(t, v_vtype(t, h), VT_LEN)))
-          return true;
-      }
+    const int a1 = d.x;
+    if (a1 >= 0 && lane_count(t, a1) > 0) {
+      int h = t.lane_start[a1];
+      float dist_f = __int_as_float(d.w) - t.pos[h];
+      if (t.speed[h] >= kHaltSpeed &&
+          time_conflict(seen, v, cross, dist_f, t.speed[h], via_len - __int_as_float(d.w) + VTT(t, v_vtype(t, h), VT_LEN)))
+        return true;
     }
   }
   return false;
@@ -283,20 +301,20 @@ __device__ __forceinline__ float lane_occ(const Tile& t, int l) {
 // stop-line decision for link k, `seen` metres ahead of vehicle i (hop 0 = the link at the end of its lane).
 // `binds`: stopping in front of the link would bind the speed now -- right of way and keep-clear of a link further
 // ahead are only evaluated then (short lanes are crossed within one tick, so hop 0 alone is not enough).
-RS_HEAVY bool must_stop(const RsScenario& sc, const Tile& t, int i, int k, float seen, int hop, int cursor, bool binds) {
+RS_HEAVY bool must_stop(const DevScenario& sc, const Tile& t, int i, int k, float seen, int hop, int cursor, bool binds) {
   int vt = v_vtype(t, i);
   float len = VTT(t, vt, VT_LEN), decel = VTT(t, vt, VT_DECEL);
   float v = t.speed[i];
-  int from = __ldg(sc.link_from + k);
-  const bool from_internal = __ldg(sc.lane_internal + from) != 0;
+  int from = __ldg(&sc.link_rec[k].from);
+  const bool from_internal = __ldg(&sc.lane_rec[from].internal) != 0;
   int yield_link = -1;          // entry link whose foes must be checked (one call site for link_blocked)
   float cross = 0.0f;
   int st = 0;
   if (from_internal) {
-    int p = __ldg(sc.link_parent + k);
-    if (!((hop == 0 || binds) && p >= 0 && __ldg(sc.link_cont + p) && __ldg(sc.link_via + p) == from)) return false;
+    int p = __ldg(&sc.link_rec[k].parent);
+    if (!((hop == 0 || binds) && p >= 0 && __ldg(&sc.link_rec[p].cont) && __ldg(&sc.link_rec[p].via) == from)) return false;
     yield_link = p;
-    cross = __ldg(sc.link_via_len + p) - __ldg(sc.lane_len + from) + len;
+    cross = __ldg(&sc.link_rec[p].via_len) - __ldg(&sc.lane_rec[from].len) + len;
   } else {
     st = state_now(sc, t, k);
     if (st == 'r' || st == 'u') return true;
@@ -304,21 +322,21 @@ RS_HEAVY bool must_stop(const RsScenario& sc, const Tile& t, int i, int k, float
     if (st == 's' && !(v_wait(t, i) > 0 && seen <= 2.0f)) return true;
     if (hop != 0 && !binds) return false;
     bool minor = (st == 'g' || st == 'm' || st == '=' || st == 'Z' || st == 'w' || st == 's' || st == 'o');
-    if (!__ldg(sc.link_cont + k) && minor) { yield_link = k; cross = __ldg(sc.link_via_len + k) + len; }
+    if (!__ldg(&sc.link_rec[k].cont) && minor) { yield_link = k; cross = __ldg(&sc.link_rec[k].via_len) + len; }
   }
   if (yield_link >= 0) {
     bool b = link_blocked(sc, t, yield_link, seen, v, cross);
     if (from_internal) return b;
     if (b) return true;
   }
-  const int f0 = __ldg(sc.link_foe_off + k), f1 = __ldg(sc.link_foe_off + k + 1);
-  if (__ldg(sc.link_cont + k)) {
+  const int f0 = __ldg(&sc.link_rec[k].foe_off), f1 = __ldg(&sc.link_rec[k + 1].foe_off);
+  if (__ldg(&sc.link_rec[k].cont)) {
     // waiting slot inside the junction is taken by a STANDING vehicle (a moving one is simply followed)
-    int vl = __ldg(sc.link_via + k);
+    int vl = __ldg(&sc.link_rec[k].via);
     if (lane_count(t, vl) > 0 && t.speed[(int)t.lane_start[vl + 1] - 1] < kHaltSpeed) return true;
   } else if (yield_link < 0) {
     for (int fi = f0; fi < f1; ++fi) {
-      int li = __ldg(sc.link_last_int + __ldg(sc.foe_link + fi));
+      int li = __ldg(&sc.foe_rec[fi].last_int);
       if (li >= 0 && lane_count(t, li) > 0) return true;
     }
   }
@@ -331,12 +349,11 @@ RS_HEAVY bool must_stop(const RsScenario& sc, const Tile& t, int i, int k, float
   int cc2 = cursor + 1;
   int route = v_route(t, i);
   int cur;
-  { int via = __ldg(sc.link_via + k); cur = via >= 0 ? via : __ldg(sc.link_to + k); }
-  for (int h = 0; h < 3 && __ldg(sc.lane_internal + cur); ++h) {   // my own path through the junction
+  cur = __ldg(&sc.link_rec[k].nxt);
+  for (int h = 0; h < 3 && __ldg(&sc.lane_rec[cur].internal); ++h) {   // my own path through the junction
     if (lane_count(t, cur) > 0) { had = true; space -= lane_occ(t, cur); }
-    int k2 = __ldg(sc.lane_link_off + cur);
-    int via2 = __ldg(sc.link_via + k2);
-    cur = via2 >= 0 ? via2 : __ldg(sc.link_to + k2);
+    int k2 = __ldg(&sc.lane_rec[cur].link_off);
+    cur = __ldg(&sc.link_rec[k2].nxt);
   }
   for (int h = 0; h < 6; ++h) {
     int a = t.lane_start[cur], j = (int)t.lane_start[cur + 1] - 1;
@@ -349,8 +366,8 @@ RS_HEAVY bool must_stop(const RsScenario& sc, const Tile& t, int i, int k, float
       lengths += VTT(t, yvt, VT_LEN) + VTT(t, yvt, VT_GAP);
     }
     if (stopped) { space += (t.pos[j] - VTT(t, v_vtype(t, j), VT_LEN)) - lengths; break; }
-    const bool cur_internal = __ldg(sc.lane_internal + cur) != 0;
-    if (!cur_internal) space += __ldg(sc.lane_len + cur) - lengths;   // junction interiors are no place to stand
+    const bool cur_internal = __ldg(&sc.lane_rec[cur].internal) != 0;
+    if (!cur_internal) space += __ldg(&sc.lane_rec[cur].len) - lengths;   // junction interiors are no place to stand
     if (space >= need) return false;
     int k2 = next_link(sc, cur, route, cc2);
     if (k2 < 0) return false;
@@ -358,16 +375,15 @@ RS_HEAVY bool must_stop(const RsScenario& sc, const Tile& t, int i, int k, float
       int st2 = state_now(sc, t, k2);
       if (st2 == 'r' || st2 == 'u' || st2 == 'y') break;
     }
-    int via2 = __ldg(sc.link_via + k2);
-    cur = via2 >= 0 ? via2 : __ldg(sc.link_to + k2);
-    if (!__ldg(sc.lane_internal + cur)) cc2 += 1;
+    cur = __ldg(&sc.link_rec[k2].nxt);
+    if (!__ldg(&sc.lane_rec[cur].internal)) cc2 += 1;
   }
   return had && space < need;
 }
 
-__device__ __forceinline__ int strategic_dir(const RsScenario& sc, int route, int cursor, int lane) {
+__device__ __forceinline__ int strategic_dir(const DevScenario& sc, int route, int cursor, int lane) {
   int mask = __ldg(sc.route_mask + __ldg(sc.route_off + route) + cursor);
-  int okm = mask & 0xFF, bestm = (mask >> 8) & 0xFF, myidx = __ldg(sc.lane_index + lane);
+  int okm = mask & 0xFF, bestm = (mask >> 8) & 0xFF, myidx = __ldg(&sc.lane_rec[lane].index);
   int want = !((okm >> myidx) & 1) ? okm : (!((bestm >> myidx) & 1) ? bestm : 0);
   if (!want) return 0;
   for (int d = 1; d < 8; ++d) {
@@ -379,7 +395,7 @@ __device__ __forceinline__ int strategic_dir(const RsScenario& sc, int route, in
 
 // Plan one vehicle from the state at the start of the tick: next speed + lane it will be in
 // laterally (own lane unless a lane change / head swap was decided).
-RS_HEAVY void plan_vehicle(const RsScenario& sc, const Tile& t, int i, float& vn_out, int& target_out) {
+RS_HEAVY void plan_vehicle(const DevScenario& sc, const Tile& t, int i, float& vn_out, int& target_out) {
   int lane = v_lane(t, i);
   int rank = i - (int)t.lane_start[lane];
   int vt = v_vtype(t, i);
@@ -389,8 +405,8 @@ RS_HEAVY void plan_vehicle(const RsScenario& sc, const Tile& t, int i, float& vn
   float vcapv = VTT(t, vt, VT_VMAX);
   float v = t.speed[i], x = t.pos[i], sf = t.sf[i];
   int route = v_route(t, i), cursor = v_cursor(t, i);
-  float lane_len = __ldg(sc.lane_len + lane);
-  float vmaxl = fminf(__ldg(sc.lane_vmax + lane) * sf, vcapv);
+  float lane_len = __ldg(&sc.lane_rec[lane].len);
+  float vmaxl = fminf(__ldg(&sc.lane_rec[lane].vmax) * sf, vcapv);
   float vacc = fminf(v + accel, vmaxl);
   float vsafe = vacc, vlead_limit = vacc;
   bool wrong_lane_head = false;
@@ -416,9 +432,8 @@ RS_HEAVY void plan_vehicle(const RsScenario& sc, const Tile& t, int i, float& vn
       }
       const float vstop = max_safe_stop_speed(seen, decel, tau);
       if (must_stop(sc, t, i, k, seen, hop, cc, vstop < vsafe)) { vsafe = fminf(vsafe, vstop); break; }
-      int via = __ldg(sc.link_via + k);
-      int nxt = via >= 0 ? via : __ldg(sc.link_to + k);
-      vsafe = fminf(vsafe, free_speed(decel, seen, fminf(__ldg(sc.lane_vmax + nxt) * sf, vcapv)));
+      int nxt = __ldg(&sc.link_rec[k].nxt);
+      vsafe = fminf(vsafe, free_speed(decel, seen, fminf(__ldg(&sc.lane_rec[nxt].vmax) * sf, vcapv)));
       if (lane_count(t, nxt) > 0) {
         int tl = (int)t.lane_start[nxt + 1] - 1, tvt = v_vtype(t, tl);
         float gap = seen + (t.pos[tl] - VTT(t, tvt, VT_LEN)) - mingap;
@@ -427,14 +442,14 @@ RS_HEAVY void plan_vehicle(const RsScenario& sc, const Tile& t, int i, float& vn
         if (hop == 0) vlead_limit = fminf(vlead_limit, f);
         break;
       }
-      seen += __ldg(sc.lane_len + nxt);
-      if (!__ldg(sc.lane_internal + nxt)) cc += 1;
+      seen += __ldg(&sc.lane_rec[nxt].len);
+      if (!__ldg(&sc.lane_rec[nxt].internal)) cc += 1;
       cur = nxt;
       if (seen > la) break;
     }
   }
-  int left = __ldg(sc.lane_left + lane), right = __ldg(sc.lane_right + lane);
-  bool internal = __ldg(sc.lane_internal + lane) != 0;
+  int left = __ldg(&sc.lane_rec[lane].left), right = __ldg(&sc.lane_rec[lane].right);
+  bool internal = __ldg(&sc.lane_rec[lane].internal) != 0;
   // cooperation (LC2013 informFollower analogue): a vehicle of the neighbouring lane that MUST get into this lane
   // (its lane does not lead on) and is urgent becomes a virtual leader for everybody behind it
   if (sc.lane_change && !internal) {
@@ -452,11 +467,11 @@ RS_HEAVY void plan_vehicle(const RsScenario& sc, const Tile& t, int i, float& vn
       if (j < a) continue;
       const int ur = v_route(t, j), uc = v_cursor(t, j), uvt = v_vtype(t, j);
       const int masku = __ldg(sc.route_mask + __ldg(sc.route_off + ur) + uc);
-      if ((masku >> __ldg(sc.lane_index + nl)) & 1) continue;                      // its lane leads on: not urgent
-      if (!(__ldg(sc.lane_len + nl) - t.pos[j] < 60.0f || v_wait(t, j) > 3)) continue;
+      if ((masku >> __ldg(&sc.lane_rec[nl].index)) & 1) continue;                      // its lane leads on: not urgent
+      if (!(__ldg(&sc.lane_rec[nl].len) - t.pos[j] < 60.0f || v_wait(t, j) > 3)) continue;
       const int du = strategic_dir(sc, ur, uc, nl);
-      if ((du > 0 ? __ldg(sc.lane_left + nl) : (du < 0 ? __ldg(sc.lane_right + nl) : -1)) != lane) continue;
-      if (!(__ldg(sc.lane_perm + lane) & __ldg(sc.vtype_bit + uvt))) continue;
+      if ((du > 0 ? __ldg(&sc.lane_rec[nl].left) : (du < 0 ? __ldg(&sc.lane_rec[nl].right) : -1)) != lane) continue;
+      if (!(__ldg(&sc.lane_rec[lane].perm) & __ldg(sc.vtype_bit + uvt))) continue;
       vsafe = fminf(vsafe, follow_speed(gapu, t.speed[j], VTT(t, uvt, VT_DECEL), decel, tau));
     }
   }
@@ -474,7 +489,7 @@ RS_HEAVY void plan_vehicle(const RsScenario& sc, const Tile& t, int i, float& vn
   int target = -1;
   if (sc.lane_change && !internal && (left >= 0 || right >= 0) && x + vn <= lane_len) {
     int mask = __ldg(sc.route_mask + __ldg(sc.route_off + route) + cursor);
-    int okm = mask & 0xFF, bestm = (mask >> 8) & 0xFF, myidx = __ldg(sc.lane_index + lane);
+    int okm = mask & 0xFF, bestm = (mask >> 8) & 0xFF, myidx = __ldg(&sc.lane_rec[lane].index);
     int dir = strategic_dir(sc, route, cursor, lane);
     // strategic (must): the route cannot continue from this lane.  A lane that leads on but is not "best" only
     // makes the best lanes attractive (no speed loss needed to go there); any lane that leads on may be used to get
@@ -495,8 +510,8 @@ RS_HEAVY void plan_vehicle(const RsScenario& sc, const Tile& t, int i, float& vn
       if (d == 0) break;
       if ((d > 0) == ((t.tick & 1) != 0)) continue;   // even ticks: leftward, odd ticks: rightward
       int nl = d > 0 ? left : right;
-      if (nl < 0 || !(__ldg(sc.lane_perm + nl) & vbit)) continue;
-      const int nlidx = __ldg(sc.lane_index + nl);
+      if (nl < 0 || !(__ldg(&sc.lane_rec[nl].perm) & vbit)) continue;
+      const int nlidx = __ldg(&sc.lane_rec[nl].index);
       if (!strategic && !((okm >> nlidx) & 1)) continue;
       int a = t.lane_start[nl], b = t.lane_start[nl + 1], j = a;
       while (j < b && t.pos[j] >= x) ++j;
@@ -529,7 +544,7 @@ RS_HEAVY void plan_vehicle(const RsScenario& sc, const Tile& t, int i, float& vn
           const int pl = __ldg(sc.lane_watch_lane + w);
           if (lane_count(t, pl) == 0) continue;
           const int h = t.lane_start[pl], hvt = v_vtype(t, h);
-          const float gap = (x - len) + __ldg(sc.lane_watch_dist + w) + (__ldg(sc.lane_len + pl) - t.pos[h]) - VTT(t, hvt, VT_GAP);
+          const float gap = (x - len) + __ldg(sc.lane_watch_dist + w) + (__ldg(&sc.lane_rec[pl].len) - t.pos[h]) - VTT(t, hvt, VT_GAP);
           bool unsafe;
           if (urgent) unsafe = gap < brake_gap(t.speed[h], fmaxf(VTT(t, hvt, VT_DECEL), kEmergencyDecel), 1.0f);
           else {
@@ -542,10 +557,9 @@ RS_HEAVY void plan_vehicle(const RsScenario& sc, const Tile& t, int i, float& vn
           for (int hop = 0; hop < 4; ++hop) {
             const int k = hop == 0 ? v_nextlink(sc, t, h, pl) : next_link(sc, cur, hr, cc);
             if (k < 0) break;
-            const int via = __ldg(sc.link_via + k);
-            const int nxt = via >= 0 ? via : __ldg(sc.link_to + k);
+            const int nxt = __ldg(&sc.link_rec[k].nxt);
             if (nxt == nl) { ok = false; break; }
-            if (!__ldg(sc.lane_internal + nxt)) cc += 1;
+            if (!__ldg(&sc.lane_rec[nxt].internal)) cc += 1;
             cur = nxt;
           }
         }
@@ -567,10 +581,10 @@ RS_HEAVY void plan_vehicle(const RsScenario& sc, const Tile& t, int i, float& vn
   if (target < 0 && wrong_lane_head && sc.lane_change && v < kHaltSpeed && lane_len - x < 1.0f) {
     int d = strategic_dir(sc, route, cursor, lane);
     int nl = d > 0 ? left : (d < 0 ? right : -1);
-    if (nl >= 0 && lane_count(t, nl) > 0 && (__ldg(sc.lane_perm + nl) & __ldg(sc.vtype_bit + vt))) {
+    if (nl >= 0 && lane_count(t, nl) > 0 && (__ldg(&sc.lane_rec[nl].perm) & __ldg(sc.vtype_bit + vt))) {
       int y = t.lane_start[nl];
-      if (t.speed[y] < kHaltSpeed && __ldg(sc.lane_len + nl) - t.pos[y] < 1.0f &&
-          (__ldg(sc.lane_perm + lane) & __ldg(sc.vtype_bit + v_vtype(t, y))) &&
+      if (t.speed[y] < kHaltSpeed && __ldg(&sc.lane_rec[nl].len) - t.pos[y] < 1.0f &&
+          (__ldg(&sc.lane_rec[lane].perm) & __ldg(sc.vtype_bit + v_vtype(t, y))) &&
           v_nextlink(sc, t, y, nl) == -2 &&
           strategic_dir(sc, v_route(t, y), v_cursor(t, y), nl) == -d) {
         target = nl;
