@@ -219,9 +219,10 @@ int rs_get_trip_records(RsSim* sim, int32_t env, int32_t* h_arrival_tick, int32_
                         float* h_time_loss, int32_t* h_depart_delay);
 int64_t rs_kernel_launches(RsSim* sim);
 /* launch shape chosen for this scenario (diagnostics / bench `config`): threads per instance, instances per CTA,
- * CTAs in the persistent grid, dynamic shared memory per CTA.  Any pointer may be NULL. */
+ * CTAs in the persistent grid, dynamic shared memory per CTA, tile buffers in shared memory (2 = ping-pong,
+ * 1 = re-sort through registers).  Any pointer may be NULL. */
 int rs_get_launch_shape(RsSim* sim, int32_t* threads_per_instance, int32_t* instances_per_cta, int32_t* grid_ctas,
-                        int32_t* smem_bytes_per_cta);
+                        int32_t* smem_bytes_per_cta, int32_t* tile_buffers);
 /* device time (ms) of the last rs_env_step's kernels, CUDA events on the launching stream */
 int rs_last_step_ms(RsSim* sim, float* ms);
 

@@ -17,6 +17,7 @@ namespace rs {
 // shared-memory carve-up (host + device agree through this struct)
 struct SmemLayout {
   int vcap, L, n_tls, S, O, SL, n_vt;
+  int single;   // one tile buffer: the per-tick re-sort goes through registers (vcap <= 2 x threads per instance)
   size_t off_bufA, off_bufB, off_vn, off_newlane, off_newidx, off_mnext, off_arr;
   size_t off_lane_start, off_start2, off_cnt2, off_mhead;
   size_t off_tls_phase, off_tls_end, off_tls_state, off_next_phase, off_origin_cur, off_origin_backlog, off_origin_cand;
@@ -26,13 +27,14 @@ struct SmemLayout {
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-__host__ __device__ inline SmemLayout make_layout(const RsScenario& sc) {
+__host__ __device__ inline SmemLayout make_layout(const DevScenario& sc) {
   SmemLayout m;
+  m.single = sc.tile_single;
   m.vcap = sc.vcap; m.L = sc.n_lanes; m.n_tls = sc.n_tls; m.S = sc.n_signals; m.O = sc.n_origins;
   m.SL = sc.n_sig_lanes; m.n_vt = sc.n_vtypes;
   size_t o = 0;
   m.off_bufA = o; o = align16(o + (size_t)kVehWords * m.vcap * 4);
-  m.off_bufB = o; o = align16(o + (size_t)kVehWords * m.vcap * 4);
+  m.off_bufB = m.single ? m.off_bufA : o; if (!m.single) o = align16(o + (size_t)kVehWords * m.vcap * 4);
   m.off_vn = o; o = align16(o + (size_t)m.vcap * 4);
   m.off_newlane = o; o = align16(o + (size_t)m.vcap * 2);
   m.off_newidx = o; o = align16(o + (size_t)m.vcap * 2);
@@ -363,7 +365,35 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
 
   // ---- S6: scatter into the other buffer; newcomers at the back of their origin lane ----
   {
-    Tile U = T; tile_bind(U, oth, m.vcap);
+    Tile U = T; tile_bind(U, oth, m.vcap);    // single-buffer mode: oth == cur, the permutation goes through registers
+    // (compiled for the 512-thread shapes only: the small-tile shapes keep the ping-pong tile and their register budget)
+    if (BLOCK >= 512 && m.single) {
+      uint32_t w[2][kVehWords]; int dst[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int i = tid + r * BLOCK;
+        dst[r] = -1;
+        if (i < n) {
+          const uint32_t nl = newlane[i];
+          if (nl != kArrived) {
+            dst[r] = (cnt2[nl] & kDirty) ? (int)newidx[i] : (int)start2[nl] + (i - (int)T.lane_start[nl]);
+            w[r][0] = __float_as_uint(T.pos[i]); w[r][1] = __float_as_uint(T.speed[i]); w[r][2] = __float_as_uint(T.sf[i]);
+            w[r][3] = __float_as_uint(T.tloss[i]); w[r][4] = (uint32_t)T.vid[i]; w[r][5] = T.wr[i]; w[r][6] = T.rc[i];
+            w[r][7] = T.meta[i]; w[r][8] = T.ed[i]; w[r][9] = (T.dl[i] & 0xFFFFu) | (nl << 16);
+          }
+        }
+      }
+      __syncthreads();   // every survivor has been read: the tile may be overwritten in place
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int d = dst[r];
+        if (d >= 0) {
+          U.pos[d] = __uint_as_float(w[r][0]); U.speed[d] = __uint_as_float(w[r][1]); U.sf[d] = __uint_as_float(w[r][2]);
+          U.tloss[d] = __uint_as_float(w[r][3]); U.vid[d] = (int32_t)w[r][4]; U.wr[d] = w[r][5]; U.rc[d] = w[r][6];
+          U.meta[d] = w[r][7]; U.ed[d] = w[r][8]; U.dl[d] = w[r][9];
+        }
+      }
+    } else {
     for (int i = tid; i < n; i += BLOCK) {
       uint32_t nl = newlane[i];
       if (nl == kArrived) continue;
@@ -372,6 +402,7 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
       U.pos[d] = T.pos[i]; U.speed[d] = T.speed[i]; U.sf[d] = T.sf[i]; U.tloss[d] = T.tloss[i];
       U.vid[d] = T.vid[i]; U.wr[d] = T.wr[i]; U.rc[d] = T.rc[i]; U.meta[d] = T.meta[i]; U.ed[d] = T.ed[i];
       U.dl[d] = (T.dl[i] & 0xFFFFu) | (nl << 16);
+    }
     }
     for (int j = tid; j < nokc; j += BLOCK) {
       const int o = oklist[j];
@@ -799,6 +830,7 @@ struct RsSim {
   int group;   // instances per CTA
   int minb;
   int carveout;
+  int smem_extra;   // RESCO_B200_SMEM_EXTRA: unused dynamic shared memory per CTA (experiments on the L1 / shared split)
   int n_sm;
   int resident_ctas;
   std::vector<void*> allocs;
@@ -851,7 +883,7 @@ static int launch_run(RsSim* s, const RunArgs& a, cudaStream_t st) {
     CK(cudaMemsetAsync(s->d.work_counter, 0, sizeof(int32_t), st));
     if (s->resident_ctas < grid) grid = s->resident_ctas;
   }
-  k_run<TPI, G, MINB><<<grid, TPI * G, (size_t)s->layout.total * G, st>>>(s->d, a);
+  k_run<TPI, G, MINB><<<grid, TPI * G, (size_t)s->layout.total * G + s->smem_extra, st>>>(s->d, a);
   s->launches += 1;
   CK(cudaGetLastError());
   return 0;
@@ -860,7 +892,7 @@ static int launch_run(RsSim* s, const RunArgs& a, cudaStream_t st) {
 // (threads per instance, instances per CTA, min CTAs/SM for __launch_bounds__: 1 = registers uncapped,
 //  1024/(TPI*G) = 64 registers per thread)
 #define RS_VARIANTS(X) X(64, 1, 1) X(64, 2, 1) X(64, 4, 1) X(64, 6, 1) X(64, 8, 1) X(32, 8, 1) X(32, 16, 1) \
-  X(128, 1, 1) X(128, 2, 1) X(128, 4, 1) X(256, 1, 1) X(256, 2, 1) X(512, 1, 1) X(512, 2, 1)
+  X(128, 1, 1) X(128, 2, 1) X(128, 4, 1) X(256, 1, 1) X(256, 2, 1) X(512, 1, 1) X(512, 2, 1) X(512, 1, 2)
 
 static int run(RsSim* s, const RunArgs& a, cudaStream_t st) {
 #define X(B, G, M) if (s->block == B && s->group == G && s->minb == M) return launch_run<B, G, M>(s, a, st);
@@ -870,7 +902,7 @@ static int run(RsSim* s, const RunArgs& a, cudaStream_t st) {
 }
 
 static int configure(RsSim* s) {
-  const int bytes = (int)s->layout.total * s->group;
+  const int bytes = (int)s->layout.total * s->group + s->smem_extra;
 #define X(B, G, M) if (s->block == B && s->group == G && s->minb == M) { \
     CK(cudaFuncSetAttribute(k_run<B, G, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); \
     if (s->carveout >= 0) CK(cudaFuncSetAttribute(k_run<B, G, M>, cudaFuncAttributePreferredSharedMemoryCarveout, s->carveout)); \
@@ -1022,26 +1054,53 @@ extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, ui
   CK(cudaMallocHost((void**)&s->h_act_pinned, sizeof(int32_t) * N * (S ? S : 1)));
   CK(cudaMallocHost((void**)&s->h_obs_pinned, sizeof(float) * N * (S ? S : 1) * 13));
   CK(cudaMallocHost((void**)&s->h_rew_pinned, sizeof(float) * N * (S ? S : 1)));
-  s->layout = make_layout(s->d.sc);
-  if (s->layout.total > (size_t)prop.sharedMemPerBlockOptin) {
-    char buf[256];
-    snprintf(buf, sizeof buf, "rs_create: instance tile needs %zu B shared memory (> %zu B per CTA); lower vcap",
-             s->layout.total, (size_t)prop.sharedMemPerBlockOptin);
-    rs_destroy(s);
-    return fail(RS_ERR_CAPACITY, buf);
-  }
   const char* eb = getenv("RESCO_B200_BLOCK");
   const char* er = getenv("RESCO_B200_REGCAP");
   const char* eg = getenv("RESCO_B200_GROUP");
-  s->group = eg ? atoi(eg) : 8;
-  while (s->group > 1 && (size_t)s->layout.total * s->group > (size_t)prop.sharedMemPerBlockOptin)
-    s->group = s->group > 8 ? 8 : (s->group == 6 ? 4 : s->group / 2);   // largest compiled shape that fits
+  const char* es = getenv("RESCO_B200_SINGLE");   // 1 / 0 force the single-buffer tile on / off; default: automatic
+  const size_t optin = (size_t)prop.sharedMemPerBlockOptin;
+  // largest compiled instances-per-CTA shape whose tiles fit the opt-in shared memory of one CTA
+  auto fit_group = [&](size_t tile, int want) {
+    int g = want;
+    while (g > 1 && tile * g > optin) g = g > 8 ? 8 : (g == 6 ? 4 : g / 2);
+    return g;
+  };
+  s->d.sc.tile_single = 0;
+  s->layout = make_layout(s->d.sc);
+  s->group = fit_group(s->layout.total, eg ? atoi(eg) : 8);
+  s->minb = 1;
+  // Big tiles (one or two instances per SM with the ping-pong tile): keep ONE tile buffer and run the per-tick
+  // re-sort through registers (needs vcap <= 2 x 512 threads).  Half the shared memory per instance doubles the
+  // instances resident per SM, which is what hides the barrier waits of the plan phase on the big maps.
+  const bool single_ok = sc->vcap <= 1024;
+  const bool single = (eb && atoi(eb) < 512) ? false : (es ? (atoi(es) != 0 && single_ok) : (single_ok && s->group <= 2));
+  if (single) {
+    s->d.sc.tile_single = 1;
+    s->layout = make_layout(s->d.sc);
+    // one instance per CTA and two independent CTAs per SM if both fit (1 KB per CTA is reserved by the driver; 64
+    // registers per thread): measured 736 k env steps/s on ingolstadt21 (2048 instances) against 645 k for two
+    // instances in lock-step in one CTA and 561 k for the ping-pong tile; grid4x4 synthetic 593 k / 508 k / 463 k
+    const bool two_ctas = 2 * (s->layout.total + 1024) <= (size_t)prop.sharedMemPerMultiprocessor;
+    s->group = fit_group(s->layout.total, eg ? atoi(eg) : (two_ctas ? 1 : 2));
+    if (s->group == 1 && two_ctas) s->minb = 2;
+  }
+  if (s->layout.total > optin) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "rs_create: instance tile needs %zu B shared memory (> %zu B per CTA); lower vcap",
+             s->layout.total, optin);
+    rs_destroy(s);
+    return fail(RS_ERR_CAPACITY, buf);
+  }
   // at least 512 threads per CTA whatever the tile size: a big map whose tile only fits once or twice per SM gets
   // 512 threads per instance, four times 128, instead of leaving the SM with two warps (measured on a B200,
   // ingolstadt21 2048 instances vcap 1024: 64 -> 126 k, 256 -> 283 k, 512 -> 404 k, 1024 -> 375 k env steps/s;
   // grid4x4 2 x 256 -> 363 k, 2 x 512 -> 377 k; cologne8 8 x 64 -> 3.55 M, 8 x 128 -> 2.53 M)
   s->block = eb ? atoi(eb) : (s->group >= 6 ? 64 : (s->group == 4 ? 128 : 512));
-  s->minb = (er ? atoi(er) != 0 : false) ? 1024 / (s->block * s->group) : 1;   // default: registers uncapped
+  if (er) s->minb = atoi(er) != 0 ? 1024 / (s->block * s->group) : 1;
+  if (s->d.sc.tile_single && (s->block < 512 || sc->vcap > 2 * s->block)) {
+    rs_destroy(s);
+    return fail(RS_ERR_INVALID, "rs_create: the single-buffer tile needs vcap <= 2 x threads per instance");
+  }
   const char* ep = getenv("RESCO_B200_PERSIST");
   s->d.persistent = ep ? atoi(ep) : 1;
   const char* et = getenv("RESCO_B200_TMA");
@@ -1051,6 +1110,8 @@ extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, ui
   TRY(dev_alloc(s, s->d.phase_clocks, 24));
   const char* ec = getenv("RESCO_B200_CARVEOUT");
   s->carveout = ec ? atoi(ec) : -1;
+  const char* ex = getenv("RESCO_B200_SMEM_EXTRA");
+  s->smem_extra = ex ? atoi(ex) : 0;
   TRY(configure(s));
   CK(cudaEventCreate(&s->ev0)); CK(cudaEventCreate(&s->ev1));
   CK(cudaEventCreateWithFlags(&s->ev_done, cudaEventDisableTiming));
@@ -1279,7 +1340,7 @@ extern "C" int rs_debug_phase_clocks(RsSim* s, unsigned long long* h_out24) {
 }
 
 extern "C" int rs_get_launch_shape(RsSim* s, int32_t* threads_per_instance, int32_t* instances_per_cta, int32_t* grid_ctas,
-                                   int32_t* smem_bytes_per_cta) {
+                                   int32_t* smem_bytes_per_cta, int32_t* tile_buffers) {
   if (!s) return fail(RS_ERR_INVALID, "rs_get_launch_shape: null sim");
   int grid = (s->d.n_env + s->group - 1) / s->group;
   if (s->d.persistent && s->resident_ctas < grid) grid = s->resident_ctas;
@@ -1287,6 +1348,7 @@ extern "C" int rs_get_launch_shape(RsSim* s, int32_t* threads_per_instance, int3
   if (instances_per_cta) *instances_per_cta = s->group;
   if (grid_ctas) *grid_ctas = grid;
   if (smem_bytes_per_cta) *smem_bytes_per_cta = (int32_t)(s->layout.total * s->group);
+  if (tile_buffers) *tile_buffers = s->d.sc.tile_single ? 1 : 2;
   return 0;
 }
 

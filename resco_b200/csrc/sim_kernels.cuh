@@ -69,6 +69,7 @@ struct DevScenario : RsScenario {                    // base-class pointers are 
   // choose_link() tabulated: [n_route_steps][8] = encode_nextlink code of the link a vehicle at route step s takes
   // from lane index j of that step's edge (0xFE route ends, 0xFD the lane does not lead on)
   const uint8_t* route_step_link;
+  int32_t tile_single;   // one tile buffer in shared memory (see SmemLayout::single)
 };
 
 // Device copy of the scenario + per-sim buffers.

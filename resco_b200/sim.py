@@ -73,7 +73,7 @@ def load_library():
     lib.rs_kernel_launches.restype = C.c_int64
     lib.rs_kernel_launches.argtypes = [C.c_void_p]
     lib.rs_last_step_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
-    lib.rs_get_launch_shape.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 4
+    lib.rs_get_launch_shape.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 5
     _LIB = lib
     return lib
 
@@ -273,10 +273,10 @@ class VecSim:
         return int(self.lib.rs_kernel_launches(self._h))
 
     def launch_shape(self) -> dict:
-        v = [C.c_int32(0) for _ in range(4)]
+        v = [C.c_int32(0) for _ in range(5)]
         _check(self.lib, self.lib.rs_get_launch_shape(self._h, *[C.byref(x) for x in v]))
         return dict(threads_per_instance=v[0].value, instances_per_cta=v[1].value, grid_ctas=v[2].value,
-                    smem_bytes_per_cta=v[3].value)
+                    smem_bytes_per_cta=v[3].value, tile_buffers=v[4].value)
 
     def last_step_ms(self) -> float:
         ms = C.c_float(0)
