@@ -38,6 +38,8 @@
 #define NUM_EPS 0.001f
 #define EMERGENCY_DECEL 9.0f
 #define LC_COOLDOWN 5
+#define COOP_MARGIN 1.0f   /* a yielding follower leaves this much more than minGap behind an urgent lane changer, so that the
+                              changer's own safety test (gap >= follower speed x 1 s) passes while the follower still creeps */
 
 typedef struct {
   float pos, speed, accel, sf, wait, rwait, tloss;
@@ -391,7 +393,7 @@ static void plan_vehicle(const OrcSim* s, Inst* in, int i, int lane, int rank) {
       int du = strategic_dir(sc, u, nl);
       if ((du > 0 ? sc->lane_left[nl] : (du < 0 ? sc->lane_right[nl] : -1)) != lane) continue;
       if (!(sc->lane_perm[lane] & sc->vtype_bit[u->vtype])) continue;
-      vsafe = fminf(vsafe, follow_speed(gapu, u->speed, VT(s, u->vtype, VT_DECEL), decel, tau));
+      vsafe = fminf(vsafe, follow_speed(gapu - COOP_MARGIN, u->speed, VT(s, u->vtype, VT_DECEL), decel, tau));
     }
   }
   float vmin_n = fmaxf(0.0f, v - decel);

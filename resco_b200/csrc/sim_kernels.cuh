@@ -33,6 +33,7 @@ constexpr float kHaltSpeed = 0.1f;
 constexpr float kNumEps = 0.001f;
 constexpr float kEmergencyDecel = 9.0f;
 constexpr int kLcCooldown = 5;
+constexpr float kCoopMargin = 1.0f;   // extra room a yielding follower leaves behind an urgent lane changer (oracle: COOP_MARGIN)
 constexpr int kVehWords = 10;      // 32-bit words per vehicle record
 constexpr int kHdrInts = 16;
 constexpr uint32_t kArrived = 0xFFFFu;
@@ -473,7 +474,7 @@ RS_HEAVY void plan_vehicle(const DevScenario& sc, const Tile& t, int i, float& v
       const int du = strategic_dir(sc, ur, uc, nl);
       if ((du > 0 ? __ldg(&sc.lane_rec[nl].left) : (du < 0 ? __ldg(&sc.lane_rec[nl].right) : -1)) != lane) continue;
       if (!(__ldg(&sc.lane_rec[lane].perm) & __ldg(sc.vtype_bit + uvt))) continue;
-      vsafe = fminf(vsafe, follow_speed(gapu, t.speed[j], VTT(t, uvt, VT_DECEL), decel, tau));
+      vsafe = fminf(vsafe, follow_speed(gapu - kCoopMargin, t.speed[j], VTT(t, uvt, VT_DECEL), decel, tau));
     }
   }
   float vmin_n = fmaxf(0.0f, v - decel);

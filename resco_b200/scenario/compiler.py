@@ -26,6 +26,7 @@ MOVEMENTS = ['S-W', 'S-S', 'S-E', 'W-N', 'W-W', 'W-S', 'N-E', 'N-N', 'N-W', 'E-S
 # link state codes (connection ``state`` attribute / tlLogic state chars) are kept as ASCII
 DIR_CODES = {c: i for i, c in enumerate("slrtLRi")}
 
+LC_HORIZON = 100.0       # metres a connected lane must at least continue beyond its edge to count as "ok"
 MAX_ROUTE_LANES = 8      # ok_mask is a u8 over lane indices of an edge
 
 
@@ -413,13 +414,20 @@ def compile_demand(arrays: Dict[str, np.ndarray], meta: Dict[str, object], idx: 
                     ok |= 1 << li
                     c[li] = ln
             cont[s] = c
-            oks[s] = ok
             cand = [li for li in range(n) if (ok >> li) & 1]
             if cand:
                 mx = max(c[li] for li in cand)
                 for li in cand:
                     if c[li] >= mx - 0.5:
                         bests[s] |= 1 << li
+                # planning horizon (cf. LC2013's look-ahead distance): a lane that does connect to the next route
+                # edge but runs out within LC_HORIZON metres beyond this edge is not a lane to stay on -- the change
+                # has to happen on THIS edge, while there is still room for it
+                ok = 0
+                for li in cand:
+                    if c[li] >= mx - 0.5 or c[li] - ln >= LC_HORIZON:
+                        ok |= 1 << li
+            oks[s] = ok
         for s, e in enumerate(edges):
             route_edges.append(e)
             route_mask.append(oks[s] | (bests[s] << 8))
