@@ -54,7 +54,14 @@ def _marshal(map_name=MAP, vcap=VCAP, synthetic_rate=0.0):
 
 
 def host_maxpressure(sc, m):
-    """Batched numpy MAXPRESSURE agent (agents/maxpressure.py + maxwave.py:18-38)."""
+    """Batched MAXPRESSURE agent over host observation buffers (agents/maxpressure.py + maxwave.py:18-38): the
+    library's host-side agent front-end (rs_host_agent_wave)."""
+    from resco_b200.sim import HostWaveAgent
+    return HostWaveAgent(sc.meta["phase_pairs"], sc.meta["valid_acts"], m.info["signal_ids"])
+
+
+def numpy_maxpressure(sc, m):
+    """The same agent in numpy (CPU-baseline workers: the oracle arm must not depend on the CUDA library)."""
     pairs = np.asarray(sc.meta["phase_pairs"], np.int64)
     va = sc.meta["valid_acts"]
     sig = m.info["signal_ids"]
@@ -80,7 +87,7 @@ def _cpu_worker(args):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     from pyoracle import OracleSim
     sc, m = _marshal()
-    agent = host_maxpressure(sc, m)
+    agent = numpy_maxpressure(sc, m)
     sim = OracleSim(m, n_inst, seed=seed)
     sim.reset(seed, first)
     sim.observe()
@@ -342,9 +349,9 @@ def run_ours(args):
             "sim_ticks_per_s": value * m.struct.step_length,
             "e2e": {"value": e2e_value, "unit": "env steps/s", "h2d_bytes_per_step": n_env * S * 4,
                     "d2h_bytes_per_step": n_env * S * 13 * 4 + n_env * S * 4, "steps": pipe_steps,
-                    "mode": "2 half-batch sims double-buffered on 2 streams (rs_env_step_host_async / rs_wait), host numpy MaxPressure agent, L2 flush inside the timed region",
+                    "mode": "2 half-batch sims double-buffered on 2 streams (rs_env_step_host_async / rs_wait), host MaxPressure agent (rs_host_agent_wave), L2 flush inside the timed region",
                     "sync_value": e2e_sync_value,
-                    "what": "per env step: pinned H2D of the actions, fused env step, D2H of mplight obs + reward, host numpy MaxPressure agent on the returned obs; wall clock; value = double-buffered (mode), sync_value = one rs_env_step_host call per step over the whole batch"},
+                    "what": "per env step: pinned H2D of the actions, fused env step, D2H of mplight obs + reward, host MaxPressure agent (rs_host_agent_wave) on the returned obs; wall clock; value = double-buffered (mode), sync_value = one rs_env_step_host call per step over the whole batch"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "rs::k_run<BLOCK> (fused env step)", "kernel_ms": k_ms,

@@ -205,6 +205,12 @@ int rs_wait(RsSim* sim);
  * pair index -1 terminates a row; ties resolve to the first maximum like the reference's strict '>'. */
 int rs_policy_maxpressure(RsSim* sim, const int32_t* h_pairs, int32_t n_pairs, const int32_t* h_order,
                           int32_t use_wave, int32_t* d_actions_out, void* stream);
+/* Host-side agent front-end: the same selection over observation rows that are already in HOST memory (what
+ * rs_env_step_host / rs_wait returned), for callers that run act -> step from host buffers.  h_obs [n_env,
+ * n_signals, obs_dim]; `skip` leading entries of a row are not pressures (1 for states.mplight -- the phase --,
+ * 0 for states.wave; agents/maxpressure.py:15-17).  No device work, no RsSim. */
+int rs_host_agent_wave(const float* h_obs, int32_t n_env, int32_t n_signals, int32_t obs_dim, int32_t skip,
+                       const int32_t* pairs, int32_t n_pairs, const int32_t* order, int32_t* h_actions);
 int rs_get_obs(RsSim* sim, RsObsView* out);
 int rs_get_stats(RsSim* sim, RsStats* h_out /* [N] */);
 /* Dump one instance's vehicles to host arrays (TraCI getters of the N=1 facade; parity tests).

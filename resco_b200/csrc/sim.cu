@@ -891,7 +891,7 @@ static int launch_run(RsSim* s, const RunArgs& a, cudaStream_t st) {
 
 // (threads per instance, instances per CTA, min CTAs/SM for __launch_bounds__: 1 = registers uncapped,
 //  1024/(TPI*G) = 64 registers per thread)
-#define RS_VARIANTS(X) X(64, 1, 1) X(64, 2, 1) X(64, 4, 1) X(64, 6, 1) X(64, 8, 1) X(32, 8, 1) X(32, 16, 1) \
+#define RS_VARIANTS(X) X(64, 1, 1) X(64, 2, 1) X(64, 4, 1) X(64, 5, 1) X(64, 6, 1) X(64, 7, 1) X(64, 8, 1) X(32, 8, 1) X(32, 16, 1) \
   X(128, 1, 1) X(128, 2, 1) X(128, 4, 1) X(256, 1, 1) X(256, 2, 1) X(512, 1, 1) X(512, 2, 1) X(512, 1, 2)
 
 static int run(RsSim* s, const RunArgs& a, cudaStream_t st) {
@@ -1062,7 +1062,7 @@ extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, ui
   // largest compiled instances-per-CTA shape whose tiles fit the opt-in shared memory of one CTA
   auto fit_group = [&](size_t tile, int want) {
     int g = want;
-    while (g > 1 && tile * g > optin) g = g > 8 ? 8 : (g == 6 ? 4 : g / 2);
+    while (g > 1 && tile * g > optin) g = g > 8 ? 8 : (g > 4 ? g - 1 : g / 2);
     return g;
   };
   s->d.sc.tile_single = 0;
@@ -1095,7 +1095,7 @@ extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, ui
   // 512 threads per instance, four times 128, instead of leaving the SM with two warps (measured on a B200,
   // ingolstadt21 2048 instances vcap 1024: 64 -> 126 k, 256 -> 283 k, 512 -> 404 k, 1024 -> 375 k env steps/s;
   // grid4x4 2 x 256 -> 363 k, 2 x 512 -> 377 k; cologne8 8 x 64 -> 3.55 M, 8 x 128 -> 2.53 M)
-  s->block = eb ? atoi(eb) : (s->group >= 6 ? 64 : (s->group == 4 ? 128 : 512));
+  s->block = eb ? atoi(eb) : (s->group >= 5 ? 64 : (s->group == 4 ? 128 : 512));
   if (er) s->minb = atoi(er) != 0 ? 1024 / (s->block * s->group) : 1;
   if (s->d.sc.tile_single && (s->block < 512 || sc->vcap > 2 * s->block)) {
     rs_destroy(s);
@@ -1240,6 +1240,33 @@ extern "C" int rs_policy_maxpressure(RsSim* s, const int32_t* h_pairs, int32_t n
   k_policy<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(s->d, s->d_pairs, n_pairs, s->d_valid, use_wave, outp);
   s->launches += 1;
   CK(cudaGetLastError());
+  return 0;
+}
+
+// Host-side agent front-end: WaveAgent.act / MaxAgent.act (agents/maxwave.py:18-38,
+// agents/maxpressure.py:13-18) over a batch of observation rows that already sit in HOST memory (the buffer
+// rs_env_step_host / rs_wait filled).  This is the caller's side of the loop, not the simulation path: it
+// touches no device state and needs no RsSim.  Same tables and tie rule (first maximum) as rs_policy_maxpressure.
+extern "C" int rs_host_agent_wave(const float* h_obs, int32_t n_env, int32_t n_signals, int32_t obs_dim, int32_t skip,
+                                  const int32_t* pairs, int32_t n_pairs, const int32_t* order, int32_t* h_actions) {
+  if (!h_obs || !pairs || !order || !h_actions || n_env < 0 || n_signals <= 0 || n_pairs <= 0 || obs_dim <= 0 || skip < 0)
+    return fail(RS_ERR_INVALID, "rs_host_agent_wave: bad arguments");
+  for (int q = 0; q < n_pairs * 2; ++q)
+    if (pairs[q] < 0 || pairs[q] + skip >= obs_dim) return fail(RS_ERR_INVALID, "rs_host_agent_wave: pair index outside the observation row");
+  for (int64_t e = 0; e < n_env; ++e) {
+    for (int sg = 0; sg < n_signals; ++sg) {
+      const float* ob = h_obs + ((size_t)e * n_signals + sg) * obs_dim + skip;
+      const int32_t* ord = order + (size_t)sg * n_pairs * 2;
+      float best = 0.0f; int act = 0; bool have = false;
+      for (int q = 0; q < n_pairs && ord[2 * q] >= 0; ++q) {
+        const int pi = ord[2 * q];
+        if (pi >= n_pairs) return fail(RS_ERR_INVALID, "rs_host_agent_wave: pair index out of range");
+        const float press = ob[pairs[2 * pi]] + ob[pairs[2 * pi + 1]];
+        if (!have || press > best) { best = press; act = ord[2 * q + 1]; have = true; }
+      }
+      h_actions[(size_t)e * n_signals + sg] = act;
+    }
+  }
   return 0;
 }
 

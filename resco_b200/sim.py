@@ -38,7 +38,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
 
 EXPORTS = ["rs_last_error", "rs_abi_version", "rs_create", "rs_destroy", "rs_reset", "rs_set_phase", "rs_tick",
-           "rs_observe", "rs_env_step", "rs_env_step_host", "rs_env_step_host_async", "rs_wait", "rs_policy_maxpressure", "rs_get_obs", "rs_get_stats",
+           "rs_observe", "rs_env_step", "rs_env_step_host", "rs_env_step_host_async", "rs_wait", "rs_policy_maxpressure", "rs_host_agent_wave", "rs_get_obs", "rs_get_stats",
            "rs_dump_vehicles", "rs_get_phases", "rs_get_trip_records", "rs_kernel_launches", "rs_last_step_ms", "rs_get_launch_shape"]
 
 
@@ -65,6 +65,8 @@ def load_library():
     lib.rs_wait.argtypes = [C.c_void_p]
     lib.rs_policy_maxpressure.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                                           C.c_void_p]
+    lib.rs_host_agent_wave.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                       C.c_void_p, C.c_void_p]
     lib.rs_get_obs.argtypes = [C.c_void_p, C.POINTER(RsObsView)]
     lib.rs_get_stats.argtypes = [C.c_void_p, C.c_void_p]
     lib.rs_dump_vehicles.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32)] + [C.c_void_p] * 13
@@ -97,6 +99,47 @@ _OBS_FIELDS = [("lane_queue", "f", "L"), ("lane_approach", "f", "L"), ("lane_tot
                ("mplight", "f", "S13"), ("wave", "f", "S12"), ("reward_wait", "f", "S"),
                ("reward_wait_norm", "f", "S"), ("reward_pressure", "f", "S"), ("sig_queue_len", "i", "S"),
                ("sig_max_queue", "i", "S")]
+
+
+def policy_tables(pairs, valid_acts, signal_ids):
+    """(pairs [n_pairs*2], order [S, n_pairs, 2], n_pairs) in the layout rs_policy_maxpressure / rs_host_agent_wave read:
+    order[s, k] = (pair index, action) in the reference's evaluation order (iteration order of valid_acts[signal],
+    agents/maxwave.py:28-36), pair index -1 terminates a row."""
+    npairs = len(pairs)
+    pr = np.ascontiguousarray(np.asarray(pairs, np.int32).reshape(-1))
+    va = np.full((len(signal_ids), npairs, 2), -1, np.int32)
+    for i, s in enumerate(signal_ids):
+        if valid_acts is None:
+            va[i, :, 0] = np.arange(npairs)
+            va[i, :, 1] = np.arange(npairs)
+        else:
+            for k, (pair_idx, action) in enumerate(valid_acts[s].items()):   # dict order == evaluation order
+                va[i, k] = (int(pair_idx), int(action))
+    return pr, np.ascontiguousarray(va), npairs
+
+
+class HostWaveAgent:
+    """Batched MAXPRESSURE / MAXWAVE for observation batches in host memory (agents/maxpressure.py, maxwave.py:18-38):
+    the act() of a caller that drives env_step_host; runs in the C library (rs_host_agent_wave), no device work."""
+
+    def __init__(self, pairs, valid_acts, signal_ids, use_wave: bool = False):
+        self.lib = load_library()
+        self.pairs, self.order, self.n_pairs = policy_tables(pairs, valid_acts, signal_ids)
+        self.S = len(signal_ids)
+        self.skip = 0 if use_wave else 1     # MaxAgent drops the phase entry of states.mplight (maxpressure.py:15-17)
+
+    def act(self, obs: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+        obs = np.ascontiguousarray(obs, np.float32)
+        n, S, D = obs.shape
+        if S != self.S:
+            raise ValueError(f"observation batch has {S} signals, agent was built for {self.S}")
+        if out is None:
+            out = np.empty((n, S), np.int32)
+        _check(self.lib, self.lib.rs_host_agent_wave(obs.ctypes.data, n, S, D, self.skip, self.pairs.ctypes.data,
+                                                     self.n_pairs, self.order.ctypes.data, out.ctypes.data))
+        return out
+
+    __call__ = act
 
 
 class VecSim:
@@ -203,17 +246,7 @@ class VecSim:
         """Batched MAXPRESSURE / MAXWAVE on the device -> [N, S] int32 CUDA tensor of actions."""
         t = self._torch
         if self._policy_tables is None:
-            npairs = len(pairs)
-            pr = np.ascontiguousarray(np.asarray(pairs, np.int32).reshape(-1))
-            va = np.full((self.S, npairs, 2), -1, np.int32)
-            for i, s in enumerate(signal_ids):
-                if valid_acts is None:
-                    va[i, :, 0] = np.arange(npairs)
-                    va[i, :, 1] = np.arange(npairs)
-                else:
-                    for k, (pair_idx, action) in enumerate(valid_acts[s].items()):   # dict order == evaluation order
-                        va[i, k] = (int(pair_idx), int(action))
-            self._policy_tables = (pr, np.ascontiguousarray(va), npairs)
+            self._policy_tables = policy_tables(pairs, valid_acts, signal_ids)
             self._policy_out = t.zeros((self.n_env, self.S), dtype=t.int32, device=f"cuda:{self.device}")
         pr, va, npairs = self._policy_tables
         _check(self.lib, self.lib.rs_policy_maxpressure(self._h, pr.ctypes.data, npairs, va.ctypes.data,

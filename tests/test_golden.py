@@ -68,3 +68,18 @@ def test_reference_golden_gpu(path):
 
 def test_goldens_present():
     assert len(GOLD) >= 8
+
+
+@pytest.mark.parametrize("case", ["cologne1_mplight_wait_maxpressure", "cologne8_mplight_wait_maxpressure"])
+def test_host_wave_agent_reproduces_reference_actions(case):
+    """rs_host_agent_wave (host-side agent front-end of the C library, no device work) over the observations the
+    reference recorded picks the actions the reference's own MAXPRESSURE agent picked (agents/maxpressure.py)."""
+    from resco_b200.sim import HostWaveAgent
+    from util import load
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", case + ".npz"))
+    meta = json.loads(bytes(z["meta"]).decode())
+    sc = load(meta["map"])
+    order = meta["ts_order"]
+    agent = HostWaveAgent(sc.meta["phase_pairs"], sc.meta["valid_acts"], order)
+    obs = np.concatenate([z["reset_obs"][None], z["obs"][:-1]]).reshape(-1, len(order), 13).astype(np.float32)
+    np.testing.assert_array_equal(agent.act(obs), z["act"])
