@@ -260,7 +260,7 @@ def run_ours(args):
     # ---- end-to-end through the host-buffer C-ABI call + host agent ----
     agent = host_maxpressure(sc, m)
     obs_h = sim.obs()["mplight"]
-    e2e_steps = max(8, min(args.steps, 60))
+    e2e_steps = max(8, min(args.steps, 100))
     if state["step"] + e2e_steps + 3 > episode_steps:
         preroll()
         obs_h = sim.obs()["mplight"]
@@ -291,8 +291,13 @@ def run_ours(args):
         for _ in range(args.preroll):
             h.env_step(h.policy_maxpressure(pairs, va, sig))
         halves.append(h)
-    pipe_steps = min(e2e_steps, episode_steps - args.preroll - 2)
+    pipe_warm = 3
+    pipe_steps = max(8, min(args.steps, episode_steps - args.preroll - pipe_warm - 2))
     obs_half = [h.obs()["mplight"] for h in halves]
+    for _ in range(pipe_warm):           # untimed: first calls allocate the page-locked host buffers of the two halves
+        for hi, (h, st) in enumerate(zip(halves, streams)):
+            h.env_step_host_async(agent(obs_half[hi]), reward_kind=0, stream=st)
+        obs_half = [h.wait()[0] for h in halves]
     barrier()
     t0 = time.perf_counter()
     for h, st, o in zip(halves, streams, obs_half):            # prime: one step in flight per half

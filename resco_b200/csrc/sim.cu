@@ -21,7 +21,7 @@ struct SmemLayout {
   size_t off_bufA, off_bufB, off_vn, off_newlane, off_newidx, off_mnext, off_arr;
   size_t off_lane_start, off_start2, off_cnt2, off_mhead;
   size_t off_tls_phase, off_tls_end, off_tls_state, off_next_phase, off_origin_cur, off_origin_backlog, off_origin_cand;
-  size_t off_vt, off_hdr, off_misc, off_obs, off_mbar, off_dirty, off_oklist;
+  size_t off_vt, off_hdr, off_misc, off_obs, off_mbar, off_dirty, off_oklist, off_occ;
   size_t total;
 };
 
@@ -61,6 +61,7 @@ __host__ __device__ inline SmemLayout make_layout(const DevScenario& sc) {
   m.off_mbar = o; o = align16(o + 16);
   m.off_dirty = o; o = align16(o + ((size_t)2 * m.vcap + (size_t)(m.O > 0 ? m.O : 1)) * 2);   // lanes touched this tick
   m.off_oklist = o; o = align16(o + (size_t)(m.O > 0 ? m.O : 1) * 2);                          // origins with a candidate
+  m.off_occ = o; o = align16(o + ((size_t)(m.L + 31) / 32 + 2) * 4);                          // lane-occupancy bits
   m.total = o;
   return m;
 }
@@ -425,7 +426,13 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
   {
     uint32_t* tmp = cur; cur = oth; oth = tmp;
     tile_bind(T, cur, m.vcap);
-    for (int dj = tid; dj < ndirty; dj += BLOCK) { const int l = dirty[dj]; cnt2[l] &= ~kDirty; mhead[l] = -1; }
+    uint32_t* occ = (uint32_t*)(smem + m.off_occ);
+    for (int dj = tid; dj < ndirty; dj += BLOCK) {
+      const int l = dirty[dj];
+      const int c = cnt2[l] & ~kDirty;
+      cnt2[l] = c; mhead[l] = -1;
+      if (c > 0) atomicOr(&occ[l >> 5], 1u << (l & 31)); else atomicAnd(&occ[l >> 5], ~(1u << (l & 31)));
+    }
     { uint16_t* t2 = T.lane_start; T.lane_start = start2; start2 = t2; }    // lane offsets ping-pong
     const int n2 = T.lane_start[L];
     if (tid == 0) {
@@ -562,6 +569,7 @@ __device__ __forceinline__ void run_instance(const DevSim& D, const RunArgs& A, 
   T.tls_end = (int32_t*)(smem + m.off_tls_end);
   T.tls_state = (int32_t*)(smem + m.off_tls_state);
   T.vt = vt;
+  T.occ = (const uint32_t*)(smem + m.off_occ);
   const uint64_t env_id = (uint64_t)(D.first_env_id + env);
   T.env_lo = (uint32_t)env_id; T.env_hi = (uint32_t)(env_id >> 32);
   T.seed_lo = (uint32_t)D.seed; T.seed_hi = (uint32_t)(D.seed >> 32);
@@ -623,6 +631,13 @@ __device__ __forceinline__ void run_instance(const DevSim& D, const RunArgs& A, 
     int32_t* cnt2 = (int32_t*)(smem + m.off_cnt2);
     int32_t* mhead = (int32_t*)(smem + m.off_mhead);
     for (int l = tid; l < m.L; l += BLOCK) { cnt2[l] = lane_count(T, l); mhead[l] = -1; }
+    // lane-occupancy bits (kept current per tick through the dirty-lane list): one ballot per 32 lanes
+    uint32_t* occ = (uint32_t*)(smem + m.off_occ);
+    for (int base = 0; base < m.L + 64; base += BLOCK) {
+      const int l = base + tid;
+      const uint32_t word = __ballot_sync(0xFFFFFFFFu, l < m.L && lane_count(T, l) > 0);
+      if ((tid & 31) == 0 && (l >> 5) < (m.L + 31) / 32 + 2) occ[l >> 5] = word;
+    }
   }
   __syncthreads();
 
@@ -958,6 +973,19 @@ extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, ui
       r.tls = sc->link_tls[k]; r.tlidx = sc->link_tlidx[k]; r.state = sc->link_state[k]; r.cont = sc->link_cont[k];
       r.via_len = sc->link_via_len[k]; r.last_int = sc->link_last_int[k]; r.parent = sc->link_parent[k];
       r.nxt = r.via >= 0 ? r.via : r.to;
+      int lo = 0x7FFFFFFF, hi = -1;
+      for (int i = sc->link_foe_off[k]; i < sc->link_foe_off[k + 1]; ++i) {
+        const int li = sc->link_last_int[sc->foe_link[i]];
+        if (li >= 0) { lo = li < lo ? li : lo; hi = li > hi ? li : hi; }
+      }
+      r.occ_word = hi < 0 ? 0 : lo >> 5; r.occ_lo = 0u; r.occ_hi = 0u;
+      if (hi >= 0 && (hi >> 5) - (lo >> 5) > 1) r.occ_word = -1;
+      else
+        for (int i = sc->link_foe_off[k]; i < sc->link_foe_off[k + 1]; ++i) {
+          const int li = sc->link_last_int[sc->foe_link[i]];
+          if (li < 0) continue;
+          if ((li >> 5) == r.occ_word) r.occ_lo |= 1u << (li & 31); else r.occ_hi |= 1u << (li & 31);
+        }
     }
     for (int i = 0; i < sc->n_foes; ++i) {
       FoeRec& r = fr[i];

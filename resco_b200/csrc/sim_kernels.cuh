@@ -56,7 +56,11 @@ struct alignas(16) LinkRec {
   int32_t from, to, via, to_edge;
   int32_t tls, tlidx, state, cont;
   float via_len; int32_t last_int, parent, foe_off;
-  int32_t nxt /* via >= 0 ? via : to */, pad0, pad1, pad2;
+  int32_t nxt /* via >= 0 ? via : to */;
+  // the last internal lanes of ALL foes of this link as a bit mask over two consecutive words of the per-instance
+  // lane-occupancy bit array (Tile::occ), so "is somebody crossing my path" is two ANDs instead of a loop over
+  // the foes; occ_word = -1 if the foes' lanes do not fit such a window (then the loop runs)
+  int32_t occ_word; uint32_t occ_lo, occ_hi;
 };                                                   // 64 B; [n_links + 1] (sentinel carries foe_off = n_foes)
 struct alignas(16) FoeRec {                          // one foe of a link, joined with what link_blocked reads of it
   int32_t link, flags, last_int, from;               // foe link f, foe_flags, link_last_int[f], link_from[f]
@@ -174,6 +178,7 @@ struct Tile {
   uint32_t* ed;    // seen_epoch (lo16) | depart tick (hi16)
   uint32_t* dl;    // depart delay (lo16) | lane (hi16)
   uint16_t* lane_start;   // [L+1]
+  const uint32_t* occ;    // [(L+31)/32 + 2] bit l = lane l holds a vehicle (state at the start of the tick)
   int32_t* tls_phase; int32_t* tls_end;
   int32_t* tls_state;     // [n_tls] offset into state_chars of the phase currently shown
   const float* vt;        // vtype table in smem
@@ -256,11 +261,14 @@ RS_HEAVY bool link_blocked(const DevScenario& sc, const Tile& t, int k, float se
   if (f0 >= f1) return false;
   const int4* rec = reinterpret_cast<const int4*>(sc.foe_rec);
   int4 a = __ldg(rec + 2 * f0);                          // {link, flags, last_int, from}
+  const int4 om = __ldg(reinterpret_cast<const int4*>(&sc.link_rec[k]) + 3);   // {nxt, occ_word, occ_lo, occ_hi}
+  const bool windowed = om.y >= 0;
+  if (windowed && (((t.occ[om.y] & (uint32_t)om.z) | (t.occ[om.y + 1] & (uint32_t)om.w)) != 0u)) return true;
   for (int fi = f0; fi < f1; ++fi) {
     const int4 c = a;
     a = __ldg(rec + 2 * (fi + 1));                       // next foe's record is in flight while this one is tested
     const int f = c.x, fl = c.y, li = c.z, a0 = c.w;
-    if (li >= 0 && lane_count(t, li) > 0) return true;   // somebody is crossing my path
+    if (!windowed && li >= 0 && lane_count(t, li) > 0) return true;   // somebody is crossing my path
     if (!(fl & 1)) continue;                             // I have right of way over f
     const bool occ0 = lane_count(t, a0) > 0;
     if (!occ0 && !(fl & 8)) continue;                    // bit 3: f has a waiting slot inside the junction
@@ -337,9 +345,14 @@ RS_HEAVY bool must_stop(const DevScenario& sc, const Tile& t, int i, int k, floa
     int vl = __ldg(&sc.link_rec[k].via);
     if (lane_count(t, vl) > 0 && t.speed[(int)t.lane_start[vl + 1] - 1] < kHaltSpeed) return true;
   } else if (yield_link < 0) {
-    for (int fi = f0; fi < f1; ++fi) {
-      int li = __ldg(&sc.foe_rec[fi].last_int);
-      if (li >= 0 && lane_count(t, li) > 0) return true;
+    const int4 om = __ldg(reinterpret_cast<const int4*>(&sc.link_rec[k]) + 3);   // {nxt, occ_word, occ_lo, occ_hi}
+    if (om.y >= 0) {
+      if (((t.occ[om.y] & (uint32_t)om.z) | (t.occ[om.y + 1] & (uint32_t)om.w)) != 0u) return true;
+    } else {
+      for (int fi = f0; fi < f1; ++fi) {
+        int li = __ldg(&sc.foe_rec[fi].last_int);
+        if (li >= 0 && lane_count(t, li) > 0) return true;
+      }
     }
   }
   // keep the junction clear (SUMO keepClear / getSpaceTillLastStanding): only links with foes, and only when a
