@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define RS_ABI_VERSION 2
+#define RS_ABI_VERSION 3
 #define RS_N_MOVEMENTS 12   /* the 12 movement keys of signal_config.py lane_sets */
 
 typedef enum RsStatus {
@@ -149,6 +149,9 @@ typedef struct RsObsView {
   const float* reward_pressure;  /* rewards.pressure */
   const int32_t* sig_queue_len;  /* [N, n_signals] calc_metrics queue_lengths */
   const int32_t* sig_max_queue;  /* calc_metrics max_queues */
+  const float* lane_arrivals;    /* [N, n_sig_lanes]  detected vehicles the signal had NOT seen at its previous observe:
+                                  * per lane |vehicles ∩ full_observation['arrivals']| (traffic_signal.py:217-224); with
+                                  * queue + approach this gives len(arrivals) / len(departures) (rewards.py:96-106) */
 } RsObsView;
 
 /* Per-instance episode statistics (utils/readXML.py:27-77 inputs). */

@@ -67,7 +67,7 @@ typedef struct {
   float* new_pos;
   int32_t* new_cursor;
   /* observation */
-  float *lane_queue, *lane_approach, *lane_total_wait, *lane_max_wait, *lane_speed_sum;
+  float *lane_queue, *lane_approach, *lane_total_wait, *lane_max_wait, *lane_speed_sum, *lane_arrivals;
   int32_t* phase_obs;
   float *mplight, *wave, *rew_wait, *rew_wait_norm, *rew_pressure;
   int32_t *sig_queue_len, *sig_max_queue;
@@ -774,7 +774,7 @@ static void observe_instance(OrcSim* s, Inst* in) {
   for (int sg = 0; sg < sc->n_signals; ++sg) {
     for (int q = sc->sig_lane_off[sg]; q < sc->sig_lane_off[sg + 1]; ++q) {
       int lane = sc->sig_lane[q];
-      float queue = 0, appr = 0, tw = 0, mw = 0, ss = 0;
+      float queue = 0, appr = 0, tw = 0, mw = 0, ss = 0, arrv = 0;
       float tdist = sc->lane_tls_dist[lane];
       for (int i = in->lane_start[lane]; i < in->lane_start[lane + 1]; ++i) {
         Veh* x = &in->veh[i];
@@ -782,7 +782,7 @@ static void observe_instance(OrcSim* s, Inst* in) {
         float dist = (sc->lane_len[lane] - x->pos) + tdist;
         if (!(dist <= sc->max_distance)) continue;                   /* detector range */
         int contiguous = (x->seen_epoch == e - 1 && x->seen_sig == sg);
-        if (!contiguous) x->rwait = 0.0f;                            /* popped on departure / never seen */
+        if (!contiguous) { x->rwait = 0.0f; arrv += 1.0f; }          /* popped on departure / never seen: an arrival */
         if (x->rwait > 0.0f) x->rwait += (float)sc->step_length;     /* `vehicle in self.waiting_times` */
         else if (x->wait > 0.0f) x->rwait = x->wait;                 /* getWaitingTime() > 0 */
         x->seen_epoch = e; x->seen_sig = sg;
@@ -791,7 +791,7 @@ static void observe_instance(OrcSim* s, Inst* in) {
         ss += x->speed;
       }
       in->lane_queue[q] = queue; in->lane_approach[q] = appr; in->lane_total_wait[q] = tw;
-      in->lane_max_wait[q] = mw; in->lane_speed_sum[q] = ss;
+      in->lane_max_wait[q] = mw; in->lane_speed_sum[q] = ss; in->lane_arrivals[q] = arrv;
     }
   }
   in->epoch += 1;
@@ -883,6 +883,7 @@ OrcSim* orc_create(const RsScenario* sc, int32_t n_env, uint64_t seed) {
     in->lane_queue = (float*)own(s, 4 * (size_t)SL); in->lane_approach = (float*)own(s, 4 * (size_t)SL);
     in->lane_total_wait = (float*)own(s, 4 * (size_t)SL); in->lane_max_wait = (float*)own(s, 4 * (size_t)SL);
     in->lane_speed_sum = (float*)own(s, 4 * (size_t)SL);
+    in->lane_arrivals = (float*)own(s, 4 * (size_t)SL);
     in->phase_obs = (int32_t*)own(s, 4 * (size_t)S);
     in->mplight = (float*)own(s, 4 * (size_t)S * 13); in->wave = (float*)own(s, 4 * (size_t)S * 12);
     in->rew_wait = (float*)own(s, 4 * (size_t)S); in->rew_wait_norm = (float*)own(s, 4 * (size_t)S);
@@ -951,7 +952,8 @@ void orc_env_step(OrcSim* s, const int32_t* actions) {
 /* host copies: each array [n_env, ...] */
 void orc_get_obs(OrcSim* s, float* lane_queue, float* lane_approach, float* lane_total_wait, float* lane_max_wait,
                  float* lane_speed_sum, int32_t* phase, float* mplight, float* wave, float* rew_wait,
-                 float* rew_wait_norm, float* rew_pressure, int32_t* sig_queue_len, int32_t* sig_max_queue) {
+                 float* rew_wait_norm, float* rew_pressure, int32_t* sig_queue_len, int32_t* sig_max_queue,
+                 float* lane_arrivals) {
   int S = s->sc.n_signals, SL = s->sc.n_sig_lanes;
   for (int e = 0; e < s->n_env; ++e) {
     const Inst* in = &s->inst[e];
@@ -963,6 +965,7 @@ void orc_get_obs(OrcSim* s, float* lane_queue, float* lane_approach, float* lane
     CP(rew_wait, in->rew_wait, S, float); CP(rew_wait_norm, in->rew_wait_norm, S, float);
     CP(rew_pressure, in->rew_pressure, S, float);
     CP(sig_queue_len, in->sig_queue_len, S, int32_t); CP(sig_max_queue, in->sig_max_queue, S, int32_t);
+    CP(lane_arrivals, in->lane_arrivals, SL, float);
 #undef CP
   }
 }

@@ -40,7 +40,7 @@ def lib():
         _LIB.orc_tick.argtypes = [C.c_void_p, C.c_int32]
         _LIB.orc_observe.argtypes = [C.c_void_p]
         _LIB.orc_env_step.argtypes = [C.c_void_p, C.c_void_p]
-        _LIB.orc_get_obs.argtypes = [C.c_void_p] + [C.c_void_p] * 13
+        _LIB.orc_get_obs.argtypes = [C.c_void_p] + [C.c_void_p] * 14
         _LIB.orc_get_stats.argtypes = [C.c_void_p, C.c_void_p]
         _LIB.orc_dump_vehicles.restype = C.c_int
         _LIB.orc_dump_vehicles.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 13
@@ -60,7 +60,7 @@ OBS_FIELDS = [("lane_queue", np.float32, "L"), ("lane_approach", np.float32, "L"
               ("lane_total_wait", np.float32, "L"), ("lane_max_wait", np.float32, "L"),
               ("lane_speed_sum", np.float32, "L"), ("phase", np.int32, "S"), ("mplight", np.float32, "S13"),
               ("wave", np.float32, "S12"), ("reward_wait", np.float32, "S"), ("reward_wait_norm", np.float32, "S"),
-              ("reward_pressure", np.float32, "S"), ("sig_queue_len", np.int32, "S"), ("sig_max_queue", np.int32, "S")]
+              ("reward_pressure", np.float32, "S"), ("sig_queue_len", np.int32, "S"), ("sig_max_queue", np.int32, "S"), ("lane_arrivals", np.float32, "L")]
 
 VEH_FIELDS = [("lane", np.int32), ("pos", np.float32), ("speed", np.float32), ("accel", np.float32),
               ("wait", np.float32), ("rwait", np.float32), ("tloss", np.float32), ("vid", np.int32),

@@ -12,7 +12,7 @@ import numpy as np
 
 from .scenario.compiler import Scenario, green_phase_indices
 
-RS_ABI_VERSION = 2
+RS_ABI_VERSION = 3
 
 _I32P = C.POINTER(C.c_int32)
 _F32P = C.POINTER(C.c_float)
@@ -62,7 +62,7 @@ class RsObsView(C.Structure):
                 ("lane_max_wait", C.c_void_p), ("lane_speed_sum", C.c_void_p), ("phase", C.c_void_p),
                 ("mplight", C.c_void_p), ("wave", C.c_void_p), ("reward_wait", C.c_void_p),
                 ("reward_wait_norm", C.c_void_p), ("reward_pressure", C.c_void_p),
-                ("sig_queue_len", C.c_void_p), ("sig_max_queue", C.c_void_p)]
+                ("sig_queue_len", C.c_void_p), ("sig_max_queue", C.c_void_p), ("lane_arrivals", C.c_void_p)]
 
 
 class RsStats(C.Structure):

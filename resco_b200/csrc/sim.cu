@@ -470,7 +470,7 @@ __device__ __forceinline__ void observe_body(const DevSim& D, const SmemLayout& 
     int lane = __ldg(sc.sig_lane + q);
     int sg = __ldg(&sc.lane_rec[lane].sig);
     float tdist = __ldg(&sc.lane_rec[lane].tls_dist), llen = __ldg(&sc.lane_rec[lane].len);
-    float queue = 0, appr = 0, tw = 0, mw = 0, ss = 0;
+    float queue = 0, appr = 0, tw = 0, mw = 0, ss = 0, arrv = 0;
     int a = T.lane_start[lane], b = T.lane_start[lane + 1];
     for (int i = a + lane_id; i < b; i += 32) {
       if (tdist < 0.0f) continue;
@@ -479,7 +479,7 @@ __device__ __forceinline__ void observe_body(const DevSim& D, const SmemLayout& 
       uint32_t w = T.wr[i], mt = T.meta[i], ed = T.ed[i];
       uint32_t rwait = w >> 16, wait = w & 0xFFFFu;
       bool contiguous = ((ed & 0xFFFFu) == eprev) && (((mt >> 16) & 0xFFu) == (uint32_t)sg) && e > 0;
-      if (!contiguous) rwait = 0;
+      if (!contiguous) { rwait = 0; arrv += 1.0f; }   // not seen by this signal at its previous observe: an arrival
       if (rwait > 0) rwait += (uint32_t)sc.step_length;
       else if (wait > 0) rwait = wait;
       if (rwait > 0xFFFFu) rwait = 0xFFFFu;
@@ -496,13 +496,14 @@ __device__ __forceinline__ void observe_body(const DevSim& D, const SmemLayout& 
       appr += __shfl_xor_sync(0xffffffffu, appr, o);
       tw += __shfl_xor_sync(0xffffffffu, tw, o);
       ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      arrv += __shfl_xor_sync(0xffffffffu, arrv, o);
       mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o));
     }
     if (lane_id == 0) {
       ob[0 * SL + q] = queue; ob[1 * SL + q] = appr; ob[2 * SL + q] = tw; ob[3 * SL + q] = mw; ob[4 * SL + q] = ss;
       size_t g = (size_t)env * SL + q;
       D.lane_queue[g] = queue; D.lane_approach[g] = appr; D.lane_total_wait[g] = tw;
-      D.lane_max_wait[g] = mw; D.lane_speed_sum[g] = ss;
+      D.lane_max_wait[g] = mw; D.lane_speed_sum[g] = ss; D.lane_arrivals[g] = arrv;
     }
   }
   __syncthreads();
@@ -1070,7 +1071,7 @@ extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, ui
   const size_t SL = sc->n_sig_lanes;
   TRY(dev_alloc(s, s->d.lane_queue, N * SL)); TRY(dev_alloc(s, s->d.lane_approach, N * SL));
   TRY(dev_alloc(s, s->d.lane_total_wait, N * SL)); TRY(dev_alloc(s, s->d.lane_max_wait, N * SL));
-  TRY(dev_alloc(s, s->d.lane_speed_sum, N * SL));
+  TRY(dev_alloc(s, s->d.lane_speed_sum, N * SL)); TRY(dev_alloc(s, s->d.lane_arrivals, N * SL));
   TRY(dev_alloc(s, s->d.phase_obs, N * S)); TRY(dev_alloc(s, s->d.mplight, N * S * 13));
   TRY(dev_alloc(s, s->d.wave, N * S * 12)); TRY(dev_alloc(s, s->d.rew_wait, N * S));
   TRY(dev_alloc(s, s->d.rew_wait_norm, N * S)); TRY(dev_alloc(s, s->d.rew_pressure, N * S));
@@ -1305,7 +1306,7 @@ extern "C" int rs_get_obs(RsSim* s, RsObsView* o) {
   o->lane_max_wait = s->d.lane_max_wait; o->lane_speed_sum = s->d.lane_speed_sum; o->phase = s->d.phase_obs;
   o->mplight = s->d.mplight; o->wave = s->d.wave; o->reward_wait = s->d.rew_wait;
   o->reward_wait_norm = s->d.rew_wait_norm; o->reward_pressure = s->d.rew_pressure;
-  o->sig_queue_len = s->d.sig_queue_len; o->sig_max_queue = s->d.sig_max_queue;
+  o->sig_queue_len = s->d.sig_queue_len; o->sig_max_queue = s->d.sig_max_queue; o->lane_arrivals = s->d.lane_arrivals;
   return 0;
 }
 

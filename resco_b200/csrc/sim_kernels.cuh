@@ -92,7 +92,7 @@ struct DevSim {
   int32_t* origin_backlog;// [N][O]
   uint32_t* veh;          // [N][kVehWords][vcap]
   // observation outputs
-  float *lane_queue, *lane_approach, *lane_total_wait, *lane_max_wait, *lane_speed_sum;  // [N][SL]
+  float *lane_queue, *lane_approach, *lane_total_wait, *lane_max_wait, *lane_speed_sum, *lane_arrivals;  // [N][SL]
   int32_t* phase_obs;     // [N][S]
   float *mplight, *wave, *rew_wait, *rew_wait_norm, *rew_pressure;
   int32_t *sig_queue_len, *sig_max_queue;

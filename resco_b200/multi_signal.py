@@ -165,6 +165,24 @@ class MultiSignal(_EnvBase):
         self.lane_sig_t
         return self._lane_slot_t
 
+    def _count_present(self):
+        """[N, S] vehicles inside the detector range per signal at the last observe (len(all_vehicles),
+        traffic_signal.py:214-224); a fresh tensor, the observation buffers are overwritten by the next step."""
+        v = self.sim.obs_view()
+        per_lane = v["lane_queue"] + v["lane_approach"]
+        if getattr(self, "_lane_to_sig_t", None) is None:
+            import torch
+            m = torch.zeros((per_lane.shape[1], len(self.signal_ids)), device=per_lane.device)
+            for s, sl in enumerate(self.sig_lane_slices):
+                m[sl, s] = 1.0
+            self._lane_to_sig_t = m
+        return per_lane @ self._lane_to_sig_t
+
+    def presence_counts(self):
+        """(vehicles per signal now, at the previous observe or None before the first step) -- what the batched FMA2C
+        manager reward needs to turn arrival counts into departures."""
+        return self._n_now, self._n_prev
+
     def mdp_config(self, key):
         """mdp_configs[key][map] with the 'supervisors' reverse map (main.py:48-70)."""
         cfg = dict(self.scenario.meta.get('mdp', {}).get(key) or {})
@@ -271,6 +289,8 @@ class MultiSignal(_EnvBase):
         self._make_signals()
         self.sim.observe()
         if self.n_env > 1:
+            self._n_prev = None
+            self._n_now = self._count_present()
             return self.state_fn.batched(self)
         self._refresh_views()
         states = self.state_fn(self.signals)
@@ -283,6 +303,7 @@ class MultiSignal(_EnvBase):
         if self.n_env > 1:
             self.sim.env_step(act)
             self._tick += self.step_length
+            self._n_prev, self._n_now = self._n_now, self._count_present()
             done = self._begin + self._tick >= self.end_time
             return self.state_fn.batched(self), self.reward_fn.batched(self), done, {'eps': self.run}
         if self.gymma:

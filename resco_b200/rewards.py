@@ -82,6 +82,62 @@ def fma2c_full(signals):
     return _fma2c(signals, 'FMA2CFull')
 
 
+def _b_fma2c(env, key):
+    """dict id -> [N] device tensor.  Workers: -(queue + coef * max_wait) summed over the signal's lanes plus alpha x
+    the same of same-region neighbours; managers: fringe arrivals + liquidity (departures - arrivals) plus alpha x
+    the neighbouring regions' (rewards.py:72-136).  len(arrivals) comes from the kernel's per-lane arrival counts
+    (``lane_arrivals``), len(departures) = vehicles at the previous observe - (vehicles now - arrivals); the previous
+    count is kept by MultiSignal (``presence_counts``)."""
+    import torch
+    from .states import _region_fringes
+    v = env.sim.obs_view()
+    dev = v["lane_queue"].device
+    cache = env.__dict__.setdefault('_fma2c_reward_plans', dict())
+    if key not in cache:
+        cfg = env.mdp_config(key)
+        signals = env.signals
+        supervisors, neighbors_of = cfg['supervisors'], cfg['management_neighbors']
+        fringes = _region_fringes(signals, cfg)
+        S, SL = len(env.signal_ids), env.sim.SL
+        managers = list(cfg['management'])
+        lane_to_sig = torch.zeros((SL, S), device=dev)            # per-lane -> per-signal sums
+        fringe_w = torch.zeros((SL, len(managers)), device=dev)   # lanes counted in a manager's fringe arrivals
+        region = torch.zeros((S, len(managers)), device=dev)      # signal -> its manager
+        for si, sid in enumerate(env.signal_ids):
+            sl = env.sig_lane_slices[si]
+            lane_to_sig[sl, si] = 1.0
+            mi = managers.index(supervisors[sid])
+            region[si, mi] = 1.0
+            for slot, lane in enumerate(signals[sid].lanes):
+                if lane in fringes[supervisors[sid]]:
+                    fringe_w[sl.start + slot, mi] = 1.0
+        nb_sig = torch.zeros((S, S), device=dev)                   # own + alpha * same-region downstream neighbours
+        for si, sid in enumerate(env.signal_ids):
+            nb_sig[si, si] += 1.0
+            for neighbor in signals[sid].downstream.values():
+                if neighbor is not None and supervisors[neighbor] == supervisors[sid]:
+                    nb_sig[env.signal_ids.index(neighbor), si] += float(cfg['alpha'])
+        nb_mgr = torch.zeros((len(managers), len(managers)), device=dev)
+        for mi, mgr in enumerate(managers):
+            nb_mgr[mi, mi] += 1.0
+            for nb in neighbors_of[mgr]:
+                nb_mgr[managers.index(nb), mi] += float(cfg['alpha'])
+        cache[key] = (float(cfg['coef']), managers, lane_to_sig, fringe_w, region, nb_sig, nb_mgr)
+    coef, managers, lane_to_sig, fringe_w, region, nb_sig, nb_mgr = cache[key]
+    own = -((v["lane_queue"] + v["lane_max_wait"] * coef) @ lane_to_sig)          # [N, S]
+    worker = own @ nb_sig
+    n_now, n_prev = env.presence_counts()
+    arrivals = v["lane_arrivals"] @ lane_to_sig
+    departures = (n_prev - (n_now - arrivals)) if n_prev is not None else torch.zeros_like(arrivals)
+    mgr_own = v["lane_arrivals"] @ fringe_w + (departures - arrivals) @ region   # [N, n_managers]
+    mgr = mgr_own @ nb_mgr
+    out = {sid: worker[:, si] for si, sid in enumerate(env.signal_ids)}
+    out.update({m: mgr[:, mi] for mi, m in enumerate(managers)})
+    return out
+
+
+fma2c.batched = lambda env: _b_fma2c(env, 'FMA2C')
+fma2c_full.batched = lambda env: _b_fma2c(env, 'FMA2CFull')
 wait.batched = lambda env: env.sim.obs_view()["reward_wait"]
 wait_norm.batched = lambda env: env.sim.obs_view()["reward_wait_norm"]
 pressure.batched = lambda env: env.sim.obs_view()["reward_pressure"]

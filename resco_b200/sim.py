@@ -98,7 +98,7 @@ _OBS_FIELDS = [("lane_queue", "f", "L"), ("lane_approach", "f", "L"), ("lane_tot
                ("lane_max_wait", "f", "L"), ("lane_speed_sum", "f", "L"), ("phase", "i", "S"),
                ("mplight", "f", "S13"), ("wave", "f", "S12"), ("reward_wait", "f", "S"),
                ("reward_wait_norm", "f", "S"), ("reward_pressure", "f", "S"), ("sig_queue_len", "i", "S"),
-               ("sig_max_queue", "i", "S")]
+               ("sig_max_queue", "i", "S"), ("lane_arrivals", "f", "L")]
 
 
 def policy_tables(pairs, valid_acts, signal_ids):

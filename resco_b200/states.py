@@ -188,7 +188,80 @@ def _b_drq(env, norm):
     return torch.stack(cols, dim=-1).view(-1, SL, 5)
 
 
+def _lane_rows(env):
+    """lane name -> row of the per-lane observation tensors ([N, n_sig_lanes], signal-major); a lane listed by two
+    signals resolves to the later one, like the reference's ``lane_wave`` dict (states.py:182-186)."""
+    rows = dict()
+    for s, sid in enumerate(env.signal_ids):
+        q0 = env.sig_lane_slices[s].start
+        for slot, lane in enumerate(env.signals[sid].lanes):
+            rows[lane] = q0 + slot
+    return rows
+
+
+def fma2c_plan(env, key, full):
+    """Static gather plan of states.fma2c / fma2c_full: every output element is
+    ``coef * clip(F[src] / div, 0, clipmax)`` with F = [wave | total_wait/28 | speed_sum/20/28 | max_wait] over the
+    per-lane rows.  Built once per env by walking the same loops as ``_fma2c`` (states.py:162-305)."""
+    cfg = env.mdp_config(key)
+    signals = env.signals
+    supervisors, neighbors_of = cfg['supervisors'], cfg['management_neighbors']
+    fringes = _region_fringes(signals, cfg)
+    rows = _lane_rows(env)
+    SL = env.sim.SL
+    WAVE, TW, SPD, MW = 0, SL, 2 * SL, 3 * SL
+    nw, cw = float(cfg['norm_wave']), float(cfg['clip_wave'])
+    manager_obs = {mgr: [(WAVE + rows[l], nw, cw, 1.0) for l in lanes] for mgr, lanes in fringes.items()}
+    plan = dict()
+    signal_wave = dict()
+    for sid, sig in signals.items():
+        items = []
+        for lane in sig.lanes:
+            q = env.sig_lane_slices[env.signal_ids.index(sid)].start + sig.lanes.index(lane)
+            items.append((WAVE + rows[lane], nw, cw, 1.0))
+            if full:            # total_wait and the speed sum are read from the signal's OWN row of the lane
+                items.append((TW + q, nw, cw, 1.0))
+                items.append((SPD + q, nw, cw, 1.0))
+        signal_wave[sid] = items
+    alpha = float(cfg['alpha'])
+    for sid, sig in signals.items():
+        items = list(signal_wave[sid])
+        for neighbor in sig.downstream.values():
+            if neighbor is not None and supervisors[neighbor] == supervisors[sid]:
+                items += [(a, b, c, alpha * d) for a, b, c, d in signal_wave[neighbor]]
+        q0 = env.sig_lane_slices[env.signal_ids.index(sid)].start
+        items += [(MW + q0 + slot, float(cfg['norm_wait']), float(cfg['clip_wait']), 1.0) for slot in range(len(sig.lanes))]
+        plan[sid] = items
+    for mgr in manager_obs:
+        items = list(manager_obs[mgr])
+        for nb in neighbors_of[mgr]:
+            items += [(a, b, c, alpha * d) for a, b, c, d in manager_obs[nb]]
+        plan[mgr] = items
+    return plan
+
+
+def _b_fma2c(env, key, full):
+    """dict id -> [N, obs_dim] device tensor (workers, then the manager pseudo-agents), float32."""
+    import torch
+    cache = env.__dict__.setdefault('_fma2c_state_plans', dict())
+    v = env.sim.obs_view()
+    dev = v["lane_queue"].device
+    if key not in cache:
+        plan = fma2c_plan(env, key, full)
+        cache[key] = {k: tuple(torch.tensor([it[j] for it in items], device=dev,
+                                            dtype=torch.int64 if j == 0 else torch.float32) for j in range(4))
+                      for k, items in plan.items()}
+    F = torch.cat([v["lane_queue"] + v["lane_approach"], v["lane_total_wait"] / 28, v["lane_speed_sum"] / 20 / 28,
+                   v["lane_max_wait"]], dim=1)
+    out = dict()
+    for k, (src, div, clipmax, coef) in cache[key].items():
+        out[k] = torch.minimum(torch.clamp_min(F[:, src] / div, 0.0), clipmax) * coef
+    return out
+
+
 mplight.batched = _b_mplight
 wave.batched = _b_wave
+fma2c.batched = lambda env: _b_fma2c(env, 'FMA2C', False)
+fma2c_full.batched = lambda env: _b_fma2c(env, 'FMA2CFull', True)
 drq.batched = lambda env: _b_drq(env, False)
 drq_norm.batched = lambda env: _b_drq(env, True)

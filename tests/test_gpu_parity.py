@@ -260,3 +260,43 @@ def test_edge_cases(case):
         assert (sg["n_active"] <= 24).all() and (sg["n_backlog"] > 0).any()
     if case == "deterministic_driver":
         assert (g.vehicles(0)["sf"] == 1.0).all()
+
+
+@pytest.mark.parametrize("map_name,key", [("cologne8", "fma2c"), ("ingolstadt7", "fma2c_full")])
+def test_batched_fma2c_matches_dict_view(map_name, key):
+    """states.fma2c*.batched / rewards.fma2c*.batched (device tensors over all instances, arrivals / departures from the
+    kernel's per-lane arrival counts) against the per-instance dict callables -- which the reference's own goldens
+    pin (tests/test_golden.py) -- on instance 0 and instance 2 of a 3-instance batch."""
+    import resco_b200.rewards as rewards
+    import resco_b200.states as states
+    from resco_b200.multi_signal import MultiSignal
+    sc = util.load(map_name)
+    mc = sc.meta["map_config"]
+    sfn, rfn = getattr(states, key), getattr(rewards, key)
+    n_env = 3
+    env = MultiSignal("t", map_name, None, sfn, rfn, step_length=mc["step_length"], yellow_length=mc["yellow_length"],
+                      log_dir=None, n_env=n_env, seed=5)
+    ng = np.array([len(env.phases[ts]) for ts in env.signal_ids])
+    for inst in (0, 2):
+        env.seed = 5
+        env.run = 0
+        obs_b = env.reset()
+        for sig in env.signals.values():
+            sig.last_step_vehicles = None
+        env._refresh_views(inst)
+        ref = sfn(env.signals)
+        assert list(obs_b.keys()) == list(ref.keys())
+        for k in ref:
+            np.testing.assert_allclose(obs_b[k][inst].cpu().numpy(), ref[k], rtol=1e-5, atol=1e-6, err_msg=f"reset obs {k}")
+        for step in range(40):
+            act = ((step // 2 + np.arange(n_env)[:, None] + np.arange(len(ng))[None, :]) % ng[None, :]).astype(np.int32)
+            obs_b, rew_b, done, _ = env.step(act)
+            env._refresh_views(inst)
+            ref_o, ref_r = sfn(env.signals), rfn(env.signals)
+            for k in ref_o:
+                np.testing.assert_allclose(obs_b[k][inst].cpu().numpy(), ref_o[k], rtol=1e-5, atol=1e-6,
+                                           err_msg=f"step {step} obs {k}")
+            for k in ref_r:
+                np.testing.assert_allclose(float(rew_b[k][inst]), float(ref_r[k]), rtol=1e-5, atol=1e-4,
+                                           err_msg=f"step {step} reward {k}")
+    env.close()

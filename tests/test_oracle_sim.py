@@ -133,3 +133,32 @@ def test_synthetic_poisson_demand_grid():
         assert not np.array_equal(a["vid"][:20], b["vid"][:20]) or not np.array_equal(a["pos"][:20], b["pos"][:20])
     # request rate scales with lambda: 300 s * 40+ lanes * p
     assert 0.6 * 4 < inserted[1] / max(inserted[0], 1) < 1.4 * 4
+
+
+def test_lane_arrivals_match_the_dict_view():
+    """The per-lane arrival counts of the fused observe (RsObsView.lane_arrivals: detected vehicles the signal had not
+    seen at its previous observe) add up to len(full_observation['arrivals']) of the per-instance dict view, and
+    vehicles(previous) - (vehicles(now) - arrivals) to len(full_observation['departures']) (traffic_signal.py:214-224)."""
+    import resco_b200.rewards as rewards
+    import resco_b200.states as states
+    from pyoracle import OracleSim
+    from resco_b200.multi_signal import MultiSignal
+    env = MultiSignal("t", "cologne8", None, states.mplight, rewards.wait, step_length=10, yellow_length=3, log_dir=None,
+                      backend=lambda m: OracleSim(m, 1, seed=0), seed=3)
+    env.reset()
+    ng = np.array([len(env.phases[ts]) for ts in env.signal_ids])
+    prev = {ts: len(env.signals[ts].full_observation['num_vehicles']) for ts in env.signal_ids}
+    seen_any = 0
+    for step in range(60):
+        env.step({ts: int((step // 3 + i) % ng[i]) for i, ts in enumerate(env.signal_ids)})
+        la = env._last_obs["lane_arrivals"][0]
+        for s, ts in enumerate(env.signal_ids):
+            full = env.signals[ts].full_observation
+            n_arr = int(la[env.sig_lane_slices[s]].sum())
+            assert n_arr == len(full['arrivals']), (step, ts)
+            now = len(full['num_vehicles'])
+            assert prev[ts] - (now - n_arr) == len(full['departures']), (step, ts)
+            prev[ts] = now
+            seen_any += n_arr
+    assert seen_any > 100
+    env.close()

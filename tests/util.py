@@ -52,7 +52,7 @@ def maxpressure_actions(sc, m, mplight):
 
 
 VEH_EXACT = ["lane", "pos", "speed", "wait", "rwait", "tloss", "vid", "vtype", "route", "cursor", "sf", "depart"]
-OBS_EXACT = ["lane_queue", "lane_approach", "lane_total_wait", "lane_max_wait", "phase", "mplight", "wave",
+OBS_EXACT = ["lane_queue", "lane_approach", "lane_total_wait", "lane_max_wait", "lane_arrivals", "phase", "mplight", "wave",
              "reward_wait", "reward_wait_norm", "reward_pressure", "sig_queue_len", "sig_max_queue"]
 
 
