@@ -188,7 +188,7 @@ def run_ours(args):
     sim.reset(args.seed, rank * n_env)
     sim.observe()
     pairs, va, sig = sc.meta["phase_pairs"], sc.meta["valid_acts"], m.info["signal_ids"]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
+    flush = torch.empty(160 << 20, dtype=torch.uint8, device=f"cuda:{local}")
     stream = torch.cuda.current_stream()
     gather_buf = None
     if args.allgather and world > 1:
@@ -345,7 +345,7 @@ def run_ours(args):
                                    + (f" / synthetic Bernoulli demand {args.synthetic_rate:g} veh/h/entry-lane" if args.synthetic_rate > 0 else ""),
                        "n_env_per_gpu": n_env, "n_env_total": total_env, "sim_ticks_per_env_step": m.struct.step_length,
                        "vcap": m.struct.vcap, **sim.launch_shape(), "persistent_grid": os.environ.get("RESCO_B200_PERSIST", "1") != "0",
-                       "l2": "flushed between timed steps (256 MiB memset, untimed)",
+                       "l2": "flushed between timed steps (160 MiB memset > 126 MB L2, untimed)",
                        "timing": "per-step CUDA events on the launching stream, summed; max over ranks",
                        "allgather_obs": bool(gather_buf is not None),
                        "avg_delay_parity_vs_sumo": "not measurable here: SUMO/libsumo is installed neither in the build container nor on the GPU box; statistical anchors against utils/avg_timeLoss.py are in DESIGN.md section 7",
