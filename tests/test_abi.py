@@ -66,3 +66,24 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert not bad.search(txt), f"{f} references the oracle"
+
+
+def test_host_wave_agent_matches_numpy_rule_and_rejects_bad_tables():
+    """rs_host_agent_wave is plain host code (no device, no RsSim): MAXWAVE over states.wave rows (skip = 0) against the
+    numpy restatement of agents/maxwave.py:18-38, and the error path for a pair index outside the observation row."""
+    import ctypes as C
+    import numpy as np
+    import util
+    from resco_b200.sim import HostWaveAgent, load_library
+    sc, m = util.marshal_map("cologne8")
+    sig = m.info["signal_ids"]
+    rng = np.random.default_rng(0)
+    wave = rng.integers(0, 6, (257, len(sig), 12)).astype(np.float32)
+    agent = HostWaveAgent(sc.meta["phase_pairs"], sc.meta["valid_acts"], sig, use_wave=True)
+    ref = util.maxpressure_actions(sc, m, np.concatenate([np.zeros_like(wave[:, :, :1]), wave], 2))
+    np.testing.assert_array_equal(agent.act(wave), ref)
+    lib = load_library()
+    out = np.zeros((1, len(sig)), np.int32)
+    rc = lib.rs_host_agent_wave(wave.ctypes.data, 1, len(sig), 5, 0, agent.pairs.ctypes.data, agent.n_pairs,
+                                agent.order.ctypes.data, out.ctypes.data)
+    assert rc < 0 and b"outside the observation row" in lib.rs_last_error()

@@ -82,3 +82,36 @@ def test_generate_config_matches_reference():
         got = generate_signal_config(t, sc.meta["controlled_links"][t])
         assert got["lane_sets"] == sc.meta["signals"][t]["lane_sets"], t
         assert got["downstream"] == sc.meta["signals"][t]["downstream"], t
+
+
+def test_lane_change_horizon_masks():
+    """route_mask per route step: 'best' lanes are a subset of the 'ok' lanes, every ok lane has a connection to the next
+    route edge, and a connected lane is only left out of 'ok' if its lane-change-free continuation beyond this edge is
+    shorter than the planning horizon (scenario/compiler.py:LC_HORIZON) -- ingolstadt7 has such lanes."""
+    import numpy as np
+    from resco_b200.scenario.compiler import LC_HORIZON
+    import util
+    assert LC_HORIZON == 100.0
+    sc = util.load("ingolstadt7")
+    a = sc.arrays
+    conn = set()
+    for k in range(len(a["link_from"])):
+        fl = int(a["link_from"][k])
+        if not a["lane_internal"][fl]:
+            conn.add((fl, int(a["link_to_edge"][k])))
+    dropped = 0
+    for r in range(len(a["route_off"]) - 1):
+        r0, r1 = int(a["route_off"][r]), int(a["route_off"][r + 1])
+        for c in range(r0, r1):
+            mask = int(a["route_mask"][c])
+            ok, best = mask & 0xFF, (mask >> 8) & 0xFF
+            assert best & ~ok == 0
+            if c + 1 == r1:
+                continue
+            e, ne = int(a["route_edge"][c]), int(a["route_edge"][c + 1])
+            l0, n = int(a["edge_lane0"][e]), min(int(a["edge_nlanes"][e]), 8)
+            connected = sum(1 << j for j in range(n) if (l0 + j, ne) in conn)
+            assert ok & ~connected == 0, "an ok lane without a connection to the next route edge"
+            assert ok != 0 or connected == 0
+            dropped += bin(connected & ~ok).count("1")
+    assert dropped > 0
