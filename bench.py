@@ -82,8 +82,8 @@ def numpy_maxpressure(sc, m):
 
 # ------------------------------------------------------------------------------------------------
 def _cpu_worker(args):
-    """One process = one core: `n_inst` oracle instances stepping `n_steps` env steps with MaxPressure."""
-    n_inst, n_steps, seed, first = args
+    """One process = one core: `n_inst` oracle instances, `warm` untimed + `n_steps` timed env steps with MaxPressure."""
+    n_inst, n_steps, seed, first, warm = args
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     from pyoracle import OracleSim
     sc, m = _marshal()
@@ -91,27 +91,31 @@ def _cpu_worker(args):
     sim = OracleSim(m, n_inst, seed=seed)
     sim.reset(seed, first)
     sim.observe()
+    for _ in range(warm):
+        sim.env_step(agent(sim.obs()["mplight"]))
     t0 = time.perf_counter()
     for _ in range(n_steps):
         sim.env_step(agent(sim.obs()["mplight"]))
     return time.perf_counter() - t0, n_inst * n_steps
 
 
-def cpu_baseline(n_steps=120, n_inst=16, cores=None):
-    """Oracle port on the host cores, bounded sample (about 10-30 s of CPU work in total)."""
+def cpu_baseline(n_steps=120, n_inst=32, cores=None, warm=90):
+    """Oracle port on the host cores, bounded sample (about 10-30 s of CPU work in total): every core steps its own
+    `n_inst` instances `n_steps` env steps after `warm` untimed ones (the GPU arm's pre-roll: both arms time the loaded network)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyoracle
     pyoracle.build()
     cores = cores or os.cpu_count() or 1
+    n_steps = max(1, min(int(n_steps), 355 - warm))      # one episode is 360 env steps
     t0 = time.perf_counter()
     with mp.get_context("fork").Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(n_inst, n_steps, 1, c * n_inst) for c in range(cores)])
+        res = pool.map(_cpu_worker, [(n_inst, n_steps, 1, c * n_inst, warm) for c in range(cores)])
     wall = time.perf_counter() - t0
     busy = max(r[0] for r in res)
     total = sum(r[1] for r in res)
     return dict(value=total / busy, unit="env steps/s", cores=cores, kind="port",
-                sample=f"{cores} procs x {n_inst} cologne8 instances x {n_steps} env steps (MaxPressure), "
-                       f"oracle/microsim.c, max-over-procs busy time {busy:.2f}s (wall {wall:.2f}s)")
+                sample=f"{cores} procs x {n_inst} cologne8 instances x {n_steps} env steps (MaxPressure, after {warm} untimed "
+                       f"steps), oracle/microsim.c, max-over-procs busy time {busy:.2f}s (wall {wall:.2f}s)")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -375,14 +379,16 @@ def run_reference(args):
     if rank != 0:
         return
     t0 = time.perf_counter()
-    cb = cpu_baseline(n_steps=max(args.steps, 1), n_inst=16)
+    # one "step" of this arm = one env step of every core's 32 instances; W warm-up steps untimed, K timed (K is capped
+    # by the episode length: the sample stays bounded whatever K the caller passes)
+    cb = cpu_baseline(n_steps=max(args.steps, 1), n_inst=32, warm=args.preroll + max(args.warmup, 0))
     wall = time.perf_counter() - t0
     world = int(os.environ.get("WORLD_SIZE", "1"))
     out = {"impl": "reference", "metric": "env steps/sec (summed instances)", "value": cb["value"],
            "unit": "env steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": 1e3 * 16 * cb["cores"] / cb["value"], "higher_is_better": True, "scaling": "weak",
+           "ms_per_step": 1e3 * 32 * cb["cores"] / cb["value"], "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"{MAP} (8 signals) / MaxPressure / bounded sample: 16 instances per host core",
+           "config": {"workload": f"{MAP} (8 signals) / MaxPressure / bounded sample: 32 instances per host core",
                       "note": "reference CPU path (MultiSignal over libsumo) unavailable: SUMO is not installed and its source is not in the reference tree; this arm is the CPU oracle port of the same algorithm (kind=port)"},
            "cpu_baseline": cb,
            "e2e": {"value": cb["value"], "unit": "env steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
