@@ -1,6 +1,9 @@
 #!/bin/bash
 # A/B of the in-tree library against every ab/*.so on the C2 bench shape (kernel-only numbers; no parity run:
-# the ab/ builds may be deliberately non-equivalent cost-attribution experiments)
+# the ab/ builds may be deliberately non-equivalent cost-attribution experiments).  Build variants here first, e.g.
+#   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -std=c++17 -shared -Xcompiler -fPIC \
+#        -DRS_BALANCED_PLAN=1 -o ab/balanced.so resco_b200/csrc/sim.cu
+# and pass EXTRA='--map ingolstadt21 --vcap 1024 --n-env 2048' for the big-map launch shape.
 cd "$(dirname "$0")/.."
 for i in 1 2; do
 for lib in resco_b200/csrc/libresco_b200.so ab/*.so; do
