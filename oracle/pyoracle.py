@@ -121,6 +121,12 @@ class OracleSim:
         lib().orc_get_obs(self._h, *ptrs)
         return out
 
+    def obs_view(self):
+        """Same keys and shapes as VecSim.obs_view(), as CPU torch tensors (copies): lets the CPU test tier run the
+        `.batched(env)` state / reward expressions of resco_b200.states / rewards on the oracle."""
+        import torch
+        return {k: torch.from_numpy(v) for k, v in self.obs().items()}
+
     def stats(self):
         st = np.zeros(self.n_env, STATS_DTYPE)
         lib().orc_get_stats(self._h, st.ctypes.data)

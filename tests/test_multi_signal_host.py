@@ -66,3 +66,50 @@ def test_unsupported_arguments_are_refused_loudly():
         _env(False, lights=["not-a-signal"])
     with pytest.raises(FileNotFoundError):
         MultiSignal("host", "no_such_map", None, states.mplight, rewards.wait, log_dir=None)
+
+
+@pytest.mark.parametrize("map_name,key,rkey", [("cologne8", "fma2c", "fma2c"), ("ingolstadt7", "fma2c_full", "fma2c_full"),
+                                               ("cologne3", "drq_norm", "wait_norm"), ("cologne8", "mplight", "pressure"),
+                                               ("cologne1", "wave", "wait"), ("ingolstadt21", "drq", "pressure")])
+def test_batched_callables_match_the_dict_view_on_the_oracle(map_name, key, rkey):
+    """`.batched(env)` tensor expressions (static gather plans; arrivals / departures from lane_arrivals and
+    presence_counts) against the per-instance dict callables the reference goldens pin, N = 3 oracle instances."""
+    import util
+    from pyoracle import OracleSim
+    sc = util.load(map_name)
+    mc = sc.meta["map_config"]
+    sfn = getattr(states, key)
+    rfn = getattr(rewards, rkey)
+    n_env = 3
+    env = MultiSignal("host", map_name, None, sfn, rfn, step_length=mc["step_length"], yellow_length=mc["yellow_length"],
+                      log_dir=None, n_env=n_env, seed=5, backend=lambda m: OracleSim(m, n_env, seed=0))
+    ng = np.array([len(env.phases[ts]) for ts in env.signal_ids])
+    for inst in (0, 2):
+        env.run = 0
+        obs_b = env.reset()
+        env._refresh_views(inst)
+        _cmp_obs(env, key, obs_b, sfn(env.signals), inst, "reset")
+        for step in range(25):
+            act = ((step // 2 + np.arange(n_env)[:, None] + np.arange(len(ng))[None, :]) % ng[None, :]).astype(np.int32)
+            obs_b, rew_b, done, _ = env.step(act)
+            env._refresh_views(inst)
+            _cmp_obs(env, key, obs_b, sfn(env.signals), inst, f"step {step}")
+            ref_r = rfn(env.signals)
+            for i, k in enumerate(ref_r):
+                got = rew_b[k][inst] if isinstance(rew_b, dict) else rew_b[inst, i]
+                np.testing.assert_allclose(float(got), float(ref_r[k]), rtol=1e-5, atol=1e-4, err_msg=f"step {step} reward {k}")
+    env.close()
+
+
+def _cmp_obs(env, key, got, ref, inst, ctx):
+    if isinstance(got, dict):
+        assert list(got.keys()) == list(ref.keys())
+        for k in ref:
+            np.testing.assert_allclose(got[k][inst].numpy(), ref[k], rtol=1e-5, atol=1e-6, err_msg=f"{ctx} obs {k}")
+    elif key.startswith("drq"):      # [N, n_sig_lanes, 5] rows, signal-major; the dict view is [1, lanes, 5] per signal
+        for s, ts in enumerate(env.signal_ids):
+            np.testing.assert_allclose(got[inst, env.sig_lane_slices[s]].numpy(), np.asarray(ref[ts])[0], rtol=1e-5,
+                                       atol=1e-6, err_msg=f"{ctx} obs {ts}")
+    else:                            # mplight / wave: [N, S, 13 | 12]
+        for s, ts in enumerate(env.signal_ids):
+            np.testing.assert_allclose(got[inst, s].numpy(), np.asarray(ref[ts]), rtol=1e-6, atol=1e-6, err_msg=f"{ctx} obs {ts}")
