@@ -259,7 +259,39 @@ def _b_fma2c(env, key, full):
     return out
 
 
+def _b_mplight_full(env):
+    """[N, S, 1 + 48] device tensor: phase, then per movement (pressure, sum(total_wait)/28, speed sum of the LAST lane
+    of the movement -- the reference resets total_speed inside its lane loop, states.py:97 --, sum(approach)/28)."""
+    import torch
+    v = env.sim.obs_view()
+    dev = v["lane_queue"].device
+    plan = env.__dict__.get('_mplight_full_plan')
+    if plan is None:
+        S, SL = len(env.signal_ids), env.sim.SL
+        lanes_to_mv = torch.zeros((SL, S * 12), device=dev)
+        last = torch.zeros((SL, S * 12), device=dev)
+        for si, sid in enumerate(env.signal_ids):
+            sig = env.signals[sid]
+            q0 = env.sig_lane_slices[si].start
+            for mi, d in enumerate(sig.lane_sets):
+                rows = [q0 + sig.lanes.index(lane) for lane in sig.lane_sets[d]]
+                for q in rows:
+                    lanes_to_mv[q, si * 12 + mi] += 1.0
+                if rows:
+                    last[rows[-1], si * 12 + mi] = 1.0
+        plan = env.__dict__['_mplight_full_plan'] = (lanes_to_mv, last)
+    lanes_to_mv, last = plan
+    N, S = v["phase"].shape
+    mp = v["mplight"]
+    wait = ((v["lane_total_wait"] / 28) @ lanes_to_mv).view(N, S, 12)
+    speed = (v["lane_speed_sum"] @ last).view(N, S, 12)
+    appr = ((v["lane_approach"] / 28) @ lanes_to_mv).view(N, S, 12)
+    per_mv = torch.stack([mp[:, :, 1:], wait, speed, appr], dim=-1).reshape(N, S, 48)
+    return torch.cat([mp[:, :, :1], per_mv], dim=-1)
+
+
 mplight.batched = _b_mplight
+mplight_full.batched = _b_mplight_full
 wave.batched = _b_wave
 fma2c.batched = lambda env: _b_fma2c(env, 'FMA2C', False)
 fma2c_full.batched = lambda env: _b_fma2c(env, 'FMA2CFull', True)

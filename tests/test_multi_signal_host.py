@@ -70,7 +70,8 @@ def test_unsupported_arguments_are_refused_loudly():
 
 @pytest.mark.parametrize("map_name,key,rkey", [("cologne8", "fma2c", "fma2c"), ("ingolstadt7", "fma2c_full", "fma2c_full"),
                                                ("cologne3", "drq_norm", "wait_norm"), ("cologne8", "mplight", "pressure"),
-                                               ("cologne1", "wave", "wait"), ("ingolstadt21", "drq", "pressure")])
+                                               ("cologne1", "wave", "wait"), ("ingolstadt21", "drq", "pressure"),
+                                               ("cologne8", "mplight_full", "pressure")])
 def test_batched_callables_match_the_dict_view_on_the_oracle(map_name, key, rkey):
     """`.batched(env)` tensor expressions (static gather plans; arrivals / departures from lane_arrivals and
     presence_counts) against the per-instance dict callables the reference goldens pin, N = 3 oracle instances."""
@@ -112,4 +113,4 @@ def _cmp_obs(env, key, got, ref, inst, ctx):
                                        atol=1e-6, err_msg=f"{ctx} obs {ts}")
     else:                            # mplight / wave: [N, S, 13 | 12]
         for s, ts in enumerate(env.signal_ids):
-            np.testing.assert_allclose(got[inst, s].numpy(), np.asarray(ref[ts]), rtol=1e-6, atol=1e-6, err_msg=f"{ctx} obs {ts}")
+            np.testing.assert_allclose(got[inst, s].numpy(), np.asarray(ref[ts]), rtol=1e-5, atol=1e-5, err_msg=f"{ctx} obs {ts}")
