@@ -139,16 +139,16 @@ class MultiSignal(_EnvBase):
         self.metrics = []
         self.connection_name = (run_name + '-' + map_name + '-' + str(len(lights)) + '-' + state_fn.__name__ + '-'
                                 + reward_fn.__name__)
-        # batched helpers for states.drq*.batched
-        if self.n_env > 1 or True:
-            a = sc.arrays
-            self._lane_sig = np.concatenate([np.full(a["sig_lane_off"][s + 1] - a["sig_lane_off"][s], s, np.int64)
-                                             for s in range(len(sig_ids))]) if sig_ids else np.zeros(0, np.int64)
-            self._lane_slot = np.concatenate([np.arange(a["sig_lane_off"][s + 1] - a["sig_lane_off"][s])
-                                              for s in range(len(sig_ids))]) if sig_ids else np.zeros(0, np.int64)
-            self.sig_lane_slices = [slice(int(a["sig_lane_off"][s]), int(a["sig_lane_off"][s + 1]))
-                                    for s in range(len(sig_ids))]
-            self._lane_sig_t = None
+        # row layout of the per-lane observation tensors ([N, n_sig_lanes], signal-major): used by calc_metrics and by
+        # the .batched state / reward expressions
+        a = sc.arrays
+        self._lane_sig = np.concatenate([np.full(a["sig_lane_off"][s + 1] - a["sig_lane_off"][s], s, np.int64)
+                                         for s in range(len(sig_ids))]) if sig_ids else np.zeros(0, np.int64)
+        self._lane_slot = np.concatenate([np.arange(a["sig_lane_off"][s + 1] - a["sig_lane_off"][s])
+                                          for s in range(len(sig_ids))]) if sig_ids else np.zeros(0, np.int64)
+        self.sig_lane_slices = [slice(int(a["sig_lane_off"][s]), int(a["sig_lane_off"][s + 1]))
+                                for s in range(len(sig_ids))]
+        self._lane_sig_t = None
 
     # ------------------------------------------------------------------------------------------
     @property
