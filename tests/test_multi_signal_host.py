@@ -114,3 +114,24 @@ def _cmp_obs(env, key, got, ref, inst, ctx):
     else:                            # mplight / wave: [N, S, 13 | 12]
         for s, ts in enumerate(env.signal_ids):
             np.testing.assert_allclose(got[inst, s].numpy(), np.asarray(ref[ts]), rtol=1e-5, atol=1e-5, err_msg=f"{ctx} obs {ts}")
+
+
+def test_epymarl_registration_mirrors_the_reference(tmp_path):
+    """resco_benchmark/__init__.py:16-61: 18 algorithms x 8 maps x 29 trials, gymma list forms, and the registered
+    kwargs construct an environment (here on the oracle) that steps."""
+    import resco_b200
+    from pyoracle import OracleSim
+    got = {}
+    ids = resco_b200.register_epymarl(register=lambda id, entry_point, kwargs: got.__setitem__(id, (entry_point, kwargs)),
+                                      log_dir=str(tmp_path))
+    assert len(ids) == len(got) == 18 * 8 * 29
+    ep, kw = got["cologne3-qmix_ns-v7"]
+    assert ep == "resco_b200.multi_signal:MultiSignal"
+    assert kw["run_name"] == "qmix_ns-tr7" and kw["gymma"] is True and kw["yellow_length"] == 4 and kw["step_length"] == 10
+    assert kw["state_fn"] is states.drq_norm and kw["reward_fn"] is rewards.wait_norm
+    env = MultiSignal(**kw, backend=lambda m: OracleSim(m, 1, seed=0), seed=1)
+    obs = env.reset()
+    assert isinstance(obs, list) and len(obs) == env.n_agents
+    obs, rew, done, info = env.step([0] * env.n_agents)
+    assert isinstance(rew, list) and done == [False] and info == {'eps': 1}
+    env.close()
