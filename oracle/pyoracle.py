@@ -31,7 +31,7 @@ def build(force: bool = False) -> str:
 def lib():
     global _LIB
     if _LIB is None:
-        _LIB = C.CDLL(build())
+        _LIB = C.CDLL(os.environ.get("ORACLE_LIB") or build())   # ORACLE_LIB: an experimental build of the rule set
         _LIB.orc_create.restype = C.c_void_p
         _LIB.orc_create.argtypes = [C.POINTER(RsScenario), C.c_int32, C.c_uint64]
         _LIB.orc_destroy.argtypes = [C.c_void_p]

@@ -10,7 +10,8 @@ Extra keyword arguments (all optional) select the batched mode:
   n_env    number of lock-step instances (default 1 -> per-instance dict view, reference semantics);
            with n_env > 1 ``step`` takes ``[N, S]`` actions and returns device tensors
            (``state_fn.batched`` / ``reward_fn.batched``) and ``done`` as a bool.
-  device   CUDA device index;   seed   base RNG seed (None -> fresh per reset, like ``--random``)
+  device   CUDA device index;   seed   base RNG seed of episode 1, +1 per reset (None -> the run index: episodes differ
+           from each other like ``--random`` runs but repeat from one process to the next)
   backend  factory ``Marshalled -> simulator`` (tests inject the CPU oracle); the default is the CUDA
            ``VecSim`` and raises if the extension or a GPU is missing -- there is no CPU fallback.
 """
@@ -345,12 +346,21 @@ class MultiSignal(_EnvBase):
                 f.write(''.join(str(line[k]) + ', ' for k in ['step', 'reward', 'max_queues', 'queue_lengths']) + '\n')
 
     def episode_stats(self):
-        """Per-instance avg delay = mean(timeLoss + departDelay) incl. unfinished and not-yet-departed
-        trips (utils/readXML.py:38-76), plus the raw counters."""
+        """Per-instance episode average of timeLoss + departDelay the way the reference computes it from the tripinfo
+        file (utils/readXML.py:27-77): over the trips that were INSERTED (finished or still running -- SUMO writes
+        both with --tripinfo-output.write-unfinished).  Trips that never got into the network are not in a tripinfo
+        file; readXML charges them ``end_time - depart`` only when the route file holds <vehicle> elements
+        (grid4x4 / arterial4x4), never for <trip> demand (cologne*, ingolstadt*).  Here the backlog of a
+        <vehicle>-demand map is charged ``now - depart`` (== the reference's rule at the end of the episode when
+        insertion is first-in-first-out; ``metrics.avg_delay_from_tripinfo`` applies the reference's rule literally to a
+        written tripinfo file).  Also returns the raw counters."""
         st = self.sim.stats()
-        n = st["n_arrived"] + st["n_active"] + st["n_backlog"]
-        delay = (st["sum_delay_arrived"] + st["sum_delay_running"] + st["sum_delay_pending"]) / np.maximum(n, 1)
-        return dict(avg_delay=delay, trips=n, stats=st)
+        n = (st["n_arrived"] + st["n_active"]).astype(np.float64)
+        total = st["sum_delay_arrived"].astype(np.float64) + st["sum_delay_running"]
+        if self.map_name in ("grid4x4", "arterial4x4"):
+            n = n + st["n_backlog"]
+            total = total + st["sum_delay_pending"]
+        return dict(avg_delay=total / np.maximum(n, 1), trips=n, stats=st)
 
     def render(self, mode='human'):
         pass

@@ -28,9 +28,23 @@ REF = {("grid4x4", "MAXWAVE"): 34.3, ("grid4x4", "MAXPRESSURE"): 52.6,
        ("cologne8", "FIXED"): 63.8, ("cologne8", "MAXWAVE"): 21.9, ("cologne8", "MAXPRESSURE"): 28.8}   # MP: first episode
 
 
-def delay(st):
+def delay_all(st):
+    """every trip whose departure time has passed, inserted or not (NOT the reference's metric: see episode_delay)"""
     n = st["n_arrived"] + st["n_active"] + st["n_backlog"]
     return (st["sum_delay_arrived"] + st["sum_delay_running"] + st["sum_delay_pending"]) / np.maximum(n, 1)
+
+
+def episode_delay(sim, sc, m, env, tmpdir):
+    """The reference's per-episode number (utils/readXML.py:27-77): write the tripinfo file of instance `env` the way
+    SUMO would (--tripinfo-output.write-unfinished) and average timeLoss + departDelay over its entries.  Trips that
+    were never inserted are NOT in a tripinfo file; readXML charges them (end_time - depart) only for <vehicle>-type
+    route files (grid4x4 / arterial4x4) and only those scheduled after the last vehicle that did depart."""
+    from resco_b200.metrics import avg_delay_from_tripinfo, write_tripinfo
+    path = os.path.join(tmpdir, f"tripinfo_{env}.xml")
+    tick = int(sim.stats()["tick"][env])
+    write_tripinfo(path, sc, sim.trip_records(env), sim.vehicles(env), tick)
+    vehicle_demand = sc.meta["map_name"] in ("grid4x4", "arterial4x4")
+    return avg_delay_from_tripinfo(path, sc, end_time=float(sc.meta["map_config"]["end_time"]), vehicle_demand=vehicle_demand)
 
 
 def run(map_name, policy, seeds, vcap=4096):
@@ -38,9 +52,9 @@ def run(map_name, policy, seeds, vcap=4096):
     mc = sc.meta["map_config"]
     T = int(mc["end_time"] - mc["start_time"])
     if policy == "FIXED":
-        m = util.marshal_map(map_name, controlled=False, vcap=vcap)[1]
+        m = util.marshal_map(map_name, controlled=False, vcap=vcap, record_trips=True)[1]
     else:
-        m = util.marshal_map(map_name, vcap=vcap, max_distance=50.0 if policy == "MAXWAVE" else 200.0)[1]
+        m = util.marshal_map(map_name, vcap=vcap, max_distance=50.0 if policy == "MAXWAVE" else 200.0, record_trips=True)[1]
     o = OracleSim(m, seeds, seed=1)
     o.reset(1, 0)
     if policy == "FIXED":
@@ -54,7 +68,10 @@ def run(map_name, policy, seeds, vcap=4096):
             x = ob["mplight"] if policy == "MAXPRESSURE" else np.concatenate([ob["mplight"][:, :, :1], ob["wave"]], 2)
             act = util.maxpressure_actions(sc, m, x)
     st = o.stats()
-    return delay(st), st
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        d = np.asarray([episode_delay(o, sc, m, e, td) for e in range(seeds)])
+    return d, st
 
 
 if __name__ == "__main__":
