@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define RS_ABI_VERSION 3
+#define RS_ABI_VERSION 4
 #define RS_N_MOVEMENTS 12   /* the 12 movement keys of signal_config.py lane_sets */
 
 typedef enum RsStatus {
@@ -133,6 +133,17 @@ typedef struct RsScenario {
   int32_t record_trips;              /* keep a per-trip arrival record (tripinfo output); trip-table demand only */
 } RsScenario;
 
+/* Optional observation tensors, off by default (rs_select_outputs): each costs its stores every env step. */
+#define RS_OUT_DRQ 1            /* states.drq          (states.py:6-31)   */
+#define RS_OUT_DRQ_NORM 2       /* states.drq_norm     (states.py:34-59)  */
+#define RS_OUT_MPLIGHT_FULL 4   /* states.mplight_full (states.py:83-113) */
+/* which tensor rs_env_step_host[_async] copies back as `h_obs` (rs_set_host_obs) */
+#define RS_HOSTOBS_MPLIGHT 0       /* [N, S, 13] */
+#define RS_HOSTOBS_WAVE 1          /* [N, S, 12] */
+#define RS_HOSTOBS_DRQ_NORM 2      /* [N, n_sig_lanes, 5] */
+#define RS_HOSTOBS_DRQ 3           /* [N, n_sig_lanes, 5] */
+#define RS_HOSTOBS_MPLIGHT_FULL 4  /* [N, S, 49] */
+
 /* Borrowed device pointers, valid until the next mutating call.  [N,...] row-major. */
 typedef struct RsObsView {
   int32_t n_env, n_signals, n_sig_lanes;
@@ -152,6 +163,12 @@ typedef struct RsObsView {
   const float* lane_arrivals;    /* [N, n_sig_lanes]  detected vehicles the signal had NOT seen at its previous observe:
                                   * per lane |vehicles ∩ full_observation['arrivals']| (traffic_signal.py:217-224); with
                                   * queue + approach this gives len(arrivals) / len(departures) (rewards.py:96-106) */
+  /* optional (RS_OUT_* bits of rs_select_outputs; stale / zero when not selected).  Rows are the signal's lanes in the
+   * order of Signal.lanes, signals back to back: a signal's [1, n_lanes, 5] block is rows sig_lane_off[s] .. of this. */
+  const float* drq;              /* [N, n_sig_lanes, 5] = [lane index == phase, approach, total_wait, queue, speed sum] */
+  const float* drq_norm;         /* [N, n_sig_lanes, 5] = [same one-hot, approach/28, total_wait/28, queue/28, speed sum/20/28] */
+  const float* mplight_full;     /* [N, n_signals, 49] = [phase, 12 x (pressure, sum(total_wait/28), speed sum of the movement's
+                                  * LAST lane (states.py:97 resets it per lane), sum(approach/28))] */
 } RsObsView;
 
 /* Per-instance episode statistics (utils/readXML.py:27-77 inputs). */
@@ -166,8 +183,11 @@ typedef struct RsStats {
   float sum_delay_running; /* same over vehicles still in the net */
   float sum_delay_pending; /* (now - depart) over not-yet-inserted trips */
   float sum_duration_arrived;
-  float sum_wait_arrived;
+  float sum_wait_arrived;  /* sum of tripinfo waitingTime (seconds with speed < 0.1 m/s) over finished trips */
   int32_t sum_active_ticks; /* sum over ticks of n_active (for the roofline V-bar) */
+  int32_t n_cap_refused;   /* insertions that had room on the road but were put off because the instance already held
+                            * `vcap` vehicles (one count per origin and tick).  SUMO has no such limit: a run in which
+                            * this is not 0 was truncated by the capacity setting, not by traffic. */
 } RsStats;
 
 typedef struct RsSim RsSim;
@@ -192,7 +212,8 @@ int rs_observe(RsSim* sim, void* stream);
  * d_actions: [N,S] int32 green-phase indices on the device. */
 int rs_env_step(RsSim* sim, const int32_t* d_actions, void* stream);
 /* Same through HOST buffers (the end-to-end call): copies actions H2D, steps, copies
- * obs/reward back; h_obs [N,S,13] mplight, h_reward [N,S] (kind: 0 wait, 1 wait_norm, 2 pressure). */
+ * obs/reward back; h_obs [N,S,13] mplight (or the tensor chosen with rs_set_host_obs), h_reward [N,S] (kind: 0 wait,
+ * 1 wait_norm, 2 pressure). */
 int rs_env_step_host(RsSim* sim, const int32_t* h_actions, float* h_obs, float* h_reward, int32_t reward_kind);
 /* Asynchronous form of rs_env_step_host: enqueues actions H2D -> env step -> obs/reward D2H on `stream` and
  * returns at once; rs_wait() blocks until that step's results are in h_obs / h_reward.  The three buffers must
@@ -220,12 +241,17 @@ int rs_get_stats(RsSim* sim, RsStats* h_out /* [N] */);
  * Arrays have room for vcap entries; returns count through n_out.  lane[i] is the lane index. */
 int rs_dump_vehicles(RsSim* sim, int32_t env, int32_t* n_out, int32_t* lane, float* pos, float* speed,
                      float* accel, float* wait, float* rwait, float* tloss, int32_t* vid, int32_t* vtype,
-                     int32_t* route, int32_t* cursor, float* sf, int32_t* depart);
+                     int32_t* route, int32_t* cursor, float* sf, int32_t* depart, float* acc_wait);
 int rs_get_phases(RsSim* sim, int32_t env, int32_t* h_tls_phase /* [n_tls] */);
 /* `--tripinfo-output` (multi_signal.py:127-129): per-trip arrival records of one instance, indexed by trip
  * (order of trip_depart/trip_route).  arrival[i] < 0: not arrived.  Needs RsScenario.record_trips. */
 int rs_get_trip_records(RsSim* sim, int32_t env, int32_t* h_arrival_tick, int32_t* h_depart_tick,
-                        float* h_time_loss, int32_t* h_depart_delay);
+                        float* h_time_loss, int32_t* h_depart_delay, float* h_waiting_time);
+/* Select the optional observation tensors (RS_OUT_* bits) the observe step writes from now on. */
+int rs_select_outputs(RsSim* sim, int32_t mask);
+/* Select the tensor rs_env_step_host[_async] returns in h_obs (RS_HOSTOBS_*; default mplight); the matching RS_OUT_*
+ * bit is switched on.  floats_per_instance (may be NULL) receives the row size of h_obs. */
+int rs_set_host_obs(RsSim* sim, int32_t kind, int32_t* floats_per_instance);
 int64_t rs_kernel_launches(RsSim* sim);
 /* launch shape chosen for this scenario (diagnostics / bench `config`): threads per instance, instances per CTA,
  * CTAs in the persistent grid, dynamic shared memory per CTA, tile buffers in shared memory (2 = ping-pong,

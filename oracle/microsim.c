@@ -42,7 +42,7 @@
                               changer's own safety test (gap >= follower speed x 1 s) passes while the follower still creeps */
 
 typedef struct {
-  float pos, speed, accel, sf, wait, rwait, tloss;
+  float pos, speed, accel, sf, wait, rwait, tloss, await;   /* await: tripinfo waitingTime (all seconds with v < 0.1) */
   int32_t vid, vtype, route, cursor, depart, ddelay, seen_epoch, seen_sig, lcc;
 } Veh;
 
@@ -70,10 +70,11 @@ typedef struct {
   float *lane_queue, *lane_approach, *lane_total_wait, *lane_max_wait, *lane_speed_sum, *lane_arrivals;
   int32_t* phase_obs;
   float *mplight, *wave, *rew_wait, *rew_wait_norm, *rew_pressure;
+  float *drq, *drq_norm, *mplight_full;
   int32_t *sig_queue_len, *sig_max_queue;
   RsStats st;
   uint64_t env_id;
-  int32_t *trip_arrival, *trip_depart_tick, *trip_ddelay; float* trip_tloss;   /* [n_trips] when record_trips */
+  int32_t *trip_arrival, *trip_depart_tick, *trip_ddelay; float *trip_tloss, *trip_wait;   /* [n_trips] when record_trips */
 } Inst;
 
 typedef struct OrcSim {
@@ -527,12 +528,12 @@ static int cmp_mover(const Inst* in, int a, int b) {
 static void record_arrival(Inst* in, const Veh* x) {
   if (in->trip_arrival) {
     in->trip_arrival[x->vid] = in->tick; in->trip_depart_tick[x->vid] = x->depart;
-    in->trip_tloss[x->vid] = x->tloss; in->trip_ddelay[x->vid] = x->ddelay;
+    in->trip_tloss[x->vid] = x->tloss; in->trip_ddelay[x->vid] = x->ddelay; in->trip_wait[x->vid] = x->await;
   }
   in->st.n_arrived += 1;
   in->st.sum_delay_arrived += x->tloss + (float)x->ddelay;
   in->st.sum_duration_arrived += (float)(in->tick - x->depart);
-  in->st.sum_wait_arrived += 0.0f;
+  in->st.sum_wait_arrived += x->await;
 }
 
 static void tick_instance(OrcSim* s, Inst* in) {
@@ -573,6 +574,7 @@ static void tick_instance(OrcSim* s, Inst* in) {
       x->accel = vn - x->speed;
       x->speed = vn;
       x->wait = vn < HALT_SPEED ? x->wait + 1.0f : 0.0f;
+      if (vn < HALT_SPEED) x->await += 1.0f;
       x->tloss += (vmaxl - vn) / vmaxl;
       if (x->lcc > 0) x->lcc -= 1;
       float p = x->pos + vn;
@@ -670,7 +672,7 @@ static void tick_instance(OrcSim* s, Inst* in) {
         ddelay = in->tick - (int)sc->trip_depart[c];
       }
       float len = VT(s, vt, VT_LEN), mingap = VT(s, vt, VT_GAP);
-      int ok = (n_after_move + nn) < sc->vcap && len <= sc->lane_len[lane];
+      int ok = len <= sc->lane_len[lane];
       int a = in->lane_start2[lane], b = in->lane_start2[lane + 1];
       if (ok && b > a) {
         const Veh* tl = &in->veh2[b - 1];
@@ -694,6 +696,9 @@ static void tick_instance(OrcSim* s, Inst* in) {
         float gap = (sc->lane_len[pl] - h->pos) + sc->origin_watch_dist[w] - VT(s, h->vtype, VT_GAP);
         if (gap < brake_gap(h->speed, VT(s, h->vtype, VT_DECEL), VT(s, h->vtype, VT_TAU))) ok = 0;
       }
+      /* capacity of the vehicle store: an insertion the road has room for but the store does not is put off and COUNTED
+       * (SUMO has no such limit; a non-zero count means the run was truncated by `vcap`) */
+      if (ok && !((n_after_move + nn) < sc->vcap)) { ok = 0; in->st.n_cap_refused += 1; }
       if (ok) {
         Veh nv; memset(&nv, 0, sizeof nv);
         nv.pos = len; nv.speed = 0.0f; nv.vid = vid; nv.vtype = vt; nv.route = route; nv.cursor = 0;
@@ -817,6 +822,27 @@ static void observe_instance(OrcSim* s, Inst* in) {
       tw += in->lane_total_wait[q]; ql += in->lane_queue[q];
       if (in->lane_queue[q] > mq) mq = in->lane_queue[q];
     }
+    /* states.drq / drq_norm (states.py:6-59): the one-hot compares the LANE index with the phase index */
+    for (int q = q0; q < q1; ++q) {
+      float oh = (q - q0) == in->phase_obs[sg] ? 1.0f : 0.0f;
+      float* d = in->drq + (size_t)q * 5; float* dn = in->drq_norm + (size_t)q * 5;
+      d[0] = oh; d[1] = in->lane_approach[q]; d[2] = in->lane_total_wait[q]; d[3] = in->lane_queue[q]; d[4] = in->lane_speed_sum[q];
+      dn[0] = oh; dn[1] = in->lane_approach[q] / 28.0f; dn[2] = in->lane_total_wait[q] / 28.0f; dn[3] = in->lane_queue[q] / 28.0f;
+      dn[4] = in->lane_speed_sum[q] / 20.0f / 28.0f;
+    }
+    /* states.mplight_full (states.py:83-113): total_speed is reset inside the lane loop -> last lane's speed sum */
+    {
+      float* mf = in->mplight_full + (size_t)sg * 49;
+      mf[0] = (float)in->phase_obs[sg];
+      for (int m = 0; m < 12; ++m) {
+        float wsum = 0, spd = 0, asum = 0;
+        for (int j = sc->mv_off[sg * 12 + m]; j < sc->mv_off[sg * 12 + m + 1]; ++j) {
+          int q = q0 + sc->mv_lane[j];
+          wsum += in->lane_total_wait[q] / 28.0f; spd = in->lane_speed_sum[q]; asum += in->lane_approach[q] / 28.0f;
+        }
+        mf[1 + 4 * m] = mp[1 + m]; mf[2 + 4 * m] = wsum; mf[3 + 4 * m] = spd; mf[4 + 4 * m] = asum;
+      }
+    }
     in->rew_wait[sg] = -tw;
     in->rew_wait_norm[sg] = fminf(fmaxf(-tw / 224.0f, -4.0f), 4.0f);
     float pr = ql;
@@ -888,10 +914,13 @@ OrcSim* orc_create(const RsScenario* sc, int32_t n_env, uint64_t seed) {
     in->mplight = (float*)own(s, 4 * (size_t)S * 13); in->wave = (float*)own(s, 4 * (size_t)S * 12);
     in->rew_wait = (float*)own(s, 4 * (size_t)S); in->rew_wait_norm = (float*)own(s, 4 * (size_t)S);
     in->rew_pressure = (float*)own(s, 4 * (size_t)S);
+    in->drq = (float*)own(s, 4 * (size_t)SL * 5); in->drq_norm = (float*)own(s, 4 * (size_t)SL * 5);
+    in->mplight_full = (float*)own(s, 4 * (size_t)S * 49);
     in->sig_queue_len = (int32_t*)own(s, 4 * (size_t)S); in->sig_max_queue = (int32_t*)own(s, 4 * (size_t)S);
     if (sc->record_trips && !sc->synthetic) {
       in->trip_arrival = (int32_t*)own(s, 4 * (size_t)sc->n_trips); in->trip_depart_tick = (int32_t*)own(s, 4 * (size_t)sc->n_trips);
       in->trip_ddelay = (int32_t*)own(s, 4 * (size_t)sc->n_trips); in->trip_tloss = (float*)own(s, 4 * (size_t)sc->n_trips);
+      in->trip_wait = (float*)own(s, 4 * (size_t)sc->n_trips);
     }
   }
   return s;
@@ -953,7 +982,7 @@ void orc_env_step(OrcSim* s, const int32_t* actions) {
 void orc_get_obs(OrcSim* s, float* lane_queue, float* lane_approach, float* lane_total_wait, float* lane_max_wait,
                  float* lane_speed_sum, int32_t* phase, float* mplight, float* wave, float* rew_wait,
                  float* rew_wait_norm, float* rew_pressure, int32_t* sig_queue_len, int32_t* sig_max_queue,
-                 float* lane_arrivals) {
+                 float* lane_arrivals, float* drq, float* drq_norm, float* mplight_full) {
   int S = s->sc.n_signals, SL = s->sc.n_sig_lanes;
   for (int e = 0; e < s->n_env; ++e) {
     const Inst* in = &s->inst[e];
@@ -966,6 +995,7 @@ void orc_get_obs(OrcSim* s, float* lane_queue, float* lane_approach, float* lane
     CP(rew_pressure, in->rew_pressure, S, float);
     CP(sig_queue_len, in->sig_queue_len, S, int32_t); CP(sig_max_queue, in->sig_max_queue, S, int32_t);
     CP(lane_arrivals, in->lane_arrivals, SL, float);
+    CP(drq, in->drq, SL * 5, float); CP(drq_norm, in->drq_norm, SL * 5, float); CP(mplight_full, in->mplight_full, S * 49, float);
 #undef CP
   }
 }
@@ -996,24 +1026,25 @@ void orc_get_stats(OrcSim* s, RsStats* out) {
 
 int orc_dump_vehicles(OrcSim* s, int32_t env, int32_t* lane, float* pos, float* speed, float* accel, float* wait,
                       float* rwait, float* tloss, int32_t* vid, int32_t* vtype, int32_t* route, int32_t* cursor,
-                      float* sf, int32_t* depart) {
+                      float* sf, int32_t* depart, float* acc_wait) {
   const Inst* in = &s->inst[env];
   for (int l = 0; l < s->sc.n_lanes; ++l)
     for (int i = in->lane_start[l]; i < in->lane_start[l + 1]; ++i) {
       const Veh* x = &in->veh[i];
       lane[i] = l; pos[i] = x->pos; speed[i] = x->speed; accel[i] = x->accel; wait[i] = x->wait; rwait[i] = x->rwait;
       tloss[i] = x->tloss; vid[i] = x->vid; vtype[i] = x->vtype; route[i] = x->route; cursor[i] = x->cursor;
-      sf[i] = x->sf; depart[i] = x->depart;
+      sf[i] = x->sf; depart[i] = x->depart; if (acc_wait) acc_wait[i] = x->await;
     }
   return in->n_veh;
 }
 
-int orc_get_trip_records(OrcSim* s, int32_t env, int32_t* arrival, int32_t* depart, float* tloss, int32_t* ddelay) {
+int orc_get_trip_records(OrcSim* s, int32_t env, int32_t* arrival, int32_t* depart, float* tloss, int32_t* ddelay, float* wait) {
   const Inst* in = &s->inst[env];
   if (!in->trip_arrival) return -1;
   size_t n = (size_t)s->sc.n_trips;
   memcpy(arrival, in->trip_arrival, 4 * n); memcpy(depart, in->trip_depart_tick, 4 * n);
   memcpy(tloss, in->trip_tloss, 4 * n); memcpy(ddelay, in->trip_ddelay, 4 * n);
+  if (wait) memcpy(wait, in->trip_wait, 4 * n);
   return 0;
 }
 

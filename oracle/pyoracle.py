@@ -40,13 +40,13 @@ def lib():
         _LIB.orc_tick.argtypes = [C.c_void_p, C.c_int32]
         _LIB.orc_observe.argtypes = [C.c_void_p]
         _LIB.orc_env_step.argtypes = [C.c_void_p, C.c_void_p]
-        _LIB.orc_get_obs.argtypes = [C.c_void_p] + [C.c_void_p] * 14
+        _LIB.orc_get_obs.argtypes = [C.c_void_p] + [C.c_void_p] * 17
         _LIB.orc_get_stats.argtypes = [C.c_void_p, C.c_void_p]
         _LIB.orc_dump_vehicles.restype = C.c_int
-        _LIB.orc_dump_vehicles.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 13
+        _LIB.orc_dump_vehicles.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 14
         _LIB.orc_get_phases.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         _LIB.orc_get_trip_records.restype = C.c_int
-        _LIB.orc_get_trip_records.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 4
+        _LIB.orc_get_trip_records.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 5
         for f in ("orc_brake_gap", "orc_max_safe_stop_speed", "orc_free_speed"):
             getattr(_LIB, f).restype = C.c_float
             getattr(_LIB, f).argtypes = [C.c_float] * 3
@@ -60,12 +60,13 @@ OBS_FIELDS = [("lane_queue", np.float32, "L"), ("lane_approach", np.float32, "L"
               ("lane_total_wait", np.float32, "L"), ("lane_max_wait", np.float32, "L"),
               ("lane_speed_sum", np.float32, "L"), ("phase", np.int32, "S"), ("mplight", np.float32, "S13"),
               ("wave", np.float32, "S12"), ("reward_wait", np.float32, "S"), ("reward_wait_norm", np.float32, "S"),
-              ("reward_pressure", np.float32, "S"), ("sig_queue_len", np.int32, "S"), ("sig_max_queue", np.int32, "S"), ("lane_arrivals", np.float32, "L")]
+              ("reward_pressure", np.float32, "S"), ("sig_queue_len", np.int32, "S"), ("sig_max_queue", np.int32, "S"), ("lane_arrivals", np.float32, "L"),
+              ("drq", np.float32, "L5"), ("drq_norm", np.float32, "L5"), ("mplight_full", np.float32, "S49")]
 
 VEH_FIELDS = [("lane", np.int32), ("pos", np.float32), ("speed", np.float32), ("accel", np.float32),
               ("wait", np.float32), ("rwait", np.float32), ("tloss", np.float32), ("vid", np.int32),
               ("vtype", np.int32), ("route", np.int32), ("cursor", np.int32), ("sf", np.float32),
-              ("depart", np.int32)]
+              ("depart", np.int32), ("acc_wait", np.float32)]
 
 
 class OracleSim:
@@ -115,11 +116,14 @@ class OracleSim:
         ptrs = []
         for name, dt, shp in OBS_FIELDS:
             shape = {"L": (self.n_env, self.SL), "S": (self.n_env, self.S), "S13": (self.n_env, self.S, 13),
-                     "S12": (self.n_env, self.S, 12)}[shp]
+                     "S12": (self.n_env, self.S, 12), "L5": (self.n_env, self.SL, 5), "S49": (self.n_env, self.S, 49)}[shp]
             out[name] = np.zeros(shape, dt)
             ptrs.append(out[name].ctypes.data)
         lib().orc_get_obs(self._h, *ptrs)
         return out
+
+    def select_outputs(self, *names):      # the oracle always computes every tensor
+        pass
 
     def obs_view(self):
         """Same keys and shapes as VecSim.obs_view(), as CPU torch tensors (copies): lets the CPU test tier run the
@@ -140,9 +144,10 @@ class OracleSim:
     def trip_records(self, env: int = 0):
         n = self.m.struct.n_trips
         out = dict(arrival=np.zeros(n, np.int32), depart=np.zeros(n, np.int32), time_loss=np.zeros(n, np.float32),
-                   depart_delay=np.zeros(n, np.int32))
+                   depart_delay=np.zeros(n, np.int32), waiting_time=np.zeros(n, np.float32))
         rc = lib().orc_get_trip_records(self._h, env, out["arrival"].ctypes.data, out["depart"].ctypes.data,
-                                        out["time_loss"].ctypes.data, out["depart_delay"].ctypes.data)
+                                        out["time_loss"].ctypes.data, out["depart_delay"].ctypes.data,
+                                        out["waiting_time"].ctypes.data)
         if rc != 0:
             raise RuntimeError("trip records were not enabled (marshal(record_trips=True))")
         return out

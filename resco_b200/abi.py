@@ -12,7 +12,7 @@ import numpy as np
 
 from .scenario.compiler import Scenario, green_phase_indices
 
-RS_ABI_VERSION = 3
+RS_ABI_VERSION = 4
 
 _I32P = C.POINTER(C.c_int32)
 _F32P = C.POINTER(C.c_float)
@@ -62,7 +62,11 @@ class RsObsView(C.Structure):
                 ("lane_max_wait", C.c_void_p), ("lane_speed_sum", C.c_void_p), ("phase", C.c_void_p),
                 ("mplight", C.c_void_p), ("wave", C.c_void_p), ("reward_wait", C.c_void_p),
                 ("reward_wait_norm", C.c_void_p), ("reward_pressure", C.c_void_p),
-                ("sig_queue_len", C.c_void_p), ("sig_max_queue", C.c_void_p), ("lane_arrivals", C.c_void_p)]
+                ("sig_queue_len", C.c_void_p), ("sig_max_queue", C.c_void_p), ("lane_arrivals", C.c_void_p),
+                ("drq", C.c_void_p), ("drq_norm", C.c_void_p), ("mplight_full", C.c_void_p)]
+
+RS_OUT_DRQ, RS_OUT_DRQ_NORM, RS_OUT_MPLIGHT_FULL = 1, 2, 4
+HOSTOBS = {"mplight": 0, "wave": 1, "drq_norm": 2, "drq": 3, "mplight_full": 4}
 
 
 class RsStats(C.Structure):
@@ -70,7 +74,7 @@ class RsStats(C.Structure):
                 ("n_arrived", C.c_int32), ("n_backlog", C.c_int32), ("anomalies", C.c_int32),
                 ("sum_delay_arrived", C.c_float), ("sum_delay_running", C.c_float),
                 ("sum_delay_pending", C.c_float), ("sum_duration_arrived", C.c_float),
-                ("sum_wait_arrived", C.c_float), ("sum_active_ticks", C.c_int32)]
+                ("sum_wait_arrived", C.c_float), ("sum_active_ticks", C.c_int32), ("n_cap_refused", C.c_int32)]
 
 
 STATS_DTYPE = np.dtype([(n, np.int32 if t is C.c_int32 else np.float32) for n, t in RsStats._fields_])
@@ -289,8 +293,8 @@ def smem_bytes(vcap: int, n_lanes: int, n_tls: int, n_signals: int, n_origins: i
     def al(x):
         return (x + 15) & ~15
     o = 0
-    o = al(o + 10 * vcap * 4)
-    o = al(o + 10 * vcap * 4)
+    o = al(o + 11 * vcap * 4)
+    o = al(o + 11 * vcap * 4)
     o = al(o + vcap * 4)
     for _ in range(4):
         o = al(o + vcap * 2)

@@ -207,6 +207,7 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
     uint32_t w = T.wr[i];
     uint32_t wait = v1 < kHaltSpeed ? (w & 0xFFFFu) + 1u : 0u;
     T.wr[i] = (w & 0xFFFF0000u) | (wait & 0xFFFFu);
+    if (v1 < kHaltSpeed) { const uint32_t aw = T.aw[i]; if ((aw & 0xFFFFu) != 0xFFFFu) T.aw[i] = aw + 1u; }
     T.tloss[i] += (vmaxl - v1) / vmaxl;
     int lcc = v_lcc(T, i);
     if (lcc > 0) lcc -= 1;
@@ -236,6 +237,7 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
       if (D.trip_rec)   // tripinfo record (multi_signal.py:127-129)
         D.trip_rec[(size_t)env * sc.n_trips + T.vid[i]] =
             make_int4(T.tick, (int)(T.ed[i] >> 16), __float_as_int(T.tloss[i]), (int)(T.dl[i] & 0xFFFFu));
+      if (D.trip_rec) D.trip_wait[(size_t)env * sc.n_trips + T.vid[i]] = (float)(T.aw[i] & 0xFFFFu);
       atomicAdd(&cnt2[l], -1);
       mark_dirty(l);
       int s = atomicAdd(&misc[M_NARR], 1);
@@ -258,7 +260,7 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
   if (tid == 0) {
     int na = misc[M_NARR];
     misc[M_NAFTER] = n - na;
-    float sd = __int_as_float(hdr[H_F_DELAY_ARR]), sdur = __int_as_float(hdr[H_F_DUR_ARR]);
+    float sd = __int_as_float(hdr[H_F_DELAY_ARR]), sdur = __int_as_float(hdr[H_F_DUR_ARR]), swait = __int_as_float(hdr[H_F_WAIT_ARR]);
     int last = -1;
     for (int k = 0; k < na; ++k) {
       int best = 0x7FFFFFFF;
@@ -266,8 +268,9 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
       last = best;
       sd += T.tloss[best] + (float)(T.dl[best] & 0xFFFFu);
       sdur += (float)(T.tick - (int)(T.ed[best] >> 16));
+      swait += (float)(T.aw[best] & 0xFFFFu);
     }
-    hdr[H_F_DELAY_ARR] = __float_as_int(sd); hdr[H_F_DUR_ARR] = __float_as_int(sdur);
+    hdr[H_F_DELAY_ARR] = __float_as_int(sd); hdr[H_F_DUR_ARR] = __float_as_int(sdur); hdr[H_F_WAIT_ARR] = __float_as_int(swait);
     hdr[H_NARR] += na;
   }
   for (int o = tid; o < m.O; o += BLOCK) {
@@ -380,7 +383,7 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
           const int ci = __ldg(sc.origin_off + o) + origin_cur[o];
           origin_backlog[o] = __float_as_int(ci < __ldg(sc.origin_off + o + 1) ? __ldg(sc.trip_depart + ci) : 3.0e38f);
         }
-      } else cand[o].ok_dd = -2;   // refused by capacity (still counts as "ok before" for later origins)
+      } else { cand[o].ok_dd = -2; atomicAdd(&hdr[H_NREF], 1); }   // refused by capacity: counted (RsStats.n_cap_refused); still "ok before" for later origins
     }
   }
   __syncthreads();
@@ -436,7 +439,7 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
             dst[r] = (cnt2[nl] & kDirty) ? (int)newidx[i] : (int)start2[nl] + (i - (int)T.lane_start[nl]);
             w[r][0] = __float_as_uint(T.pos[i]); w[r][1] = __float_as_uint(T.speed[i]); w[r][2] = __float_as_uint(T.sf[i]);
             w[r][3] = __float_as_uint(T.tloss[i]); w[r][4] = (uint32_t)T.vid[i]; w[r][5] = T.wr[i]; w[r][6] = T.rc[i];
-            w[r][7] = T.meta[i]; w[r][8] = T.ed[i]; w[r][9] = (T.dl[i] & 0xFFFFu) | (nl << 16);
+            w[r][7] = T.meta[i]; w[r][8] = T.ed[i]; w[r][9] = (T.dl[i] & 0xFFFFu) | (nl << 16); w[r][10] = T.aw[i];
           }
         }
       }
@@ -447,7 +450,7 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
         if (d >= 0) {
           U.pos[d] = __uint_as_float(w[r][0]); U.speed[d] = __uint_as_float(w[r][1]); U.sf[d] = __uint_as_float(w[r][2]);
           U.tloss[d] = __uint_as_float(w[r][3]); U.vid[d] = (int32_t)w[r][4]; U.wr[d] = w[r][5]; U.rc[d] = w[r][6];
-          U.meta[d] = w[r][7]; U.ed[d] = w[r][8]; U.dl[d] = w[r][9];
+          U.meta[d] = w[r][7]; U.ed[d] = w[r][8]; U.dl[d] = w[r][9]; U.aw[d] = w[r][10];
         }
       }
     } else {
@@ -458,7 +461,7 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
       int d = (cnt2[nl] & kDirty) ? (int)newidx[i] : (int)start2[nl] + (i - (int)T.lane_start[nl]);
       U.pos[d] = T.pos[i]; U.speed[d] = T.speed[i]; U.sf[d] = T.sf[i]; U.tloss[d] = T.tloss[i];
       U.vid[d] = T.vid[i]; U.wr[d] = T.wr[i]; U.rc[d] = T.rc[i]; U.meta[d] = T.meta[i]; U.ed[d] = T.ed[i];
-      U.dl[d] = (T.dl[i] & 0xFFFFu) | (nl << 16);
+      U.dl[d] = (T.dl[i] & 0xFFFFu) | (nl << 16); U.aw[d] = T.aw[i];
     }
     }
     for (int j = tid; j < nokc; j += BLOCK) {
@@ -472,7 +475,7 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
       U.vid[d] = c.vid; U.wr[d] = 0u; U.rc[d] = (uint32_t)c.route;
       U.meta[d] = (uint32_t)c.vt | (0xFFu << 16) | (encode_nextlink(sc, lane, choose_link(sc, lane, c.route, 0)) << 24);
       U.ed[d] = 0xFFFEu | ((uint32_t)T.tick << 16);
-      U.dl[d] = (uint32_t)(c.ok_dd & 0xFFFF) | ((uint32_t)lane << 16);
+      U.dl[d] = (uint32_t)(c.ok_dd & 0xFFFF) | ((uint32_t)lane << 16); U.aw[d] = 0u;
     }
   }
   __syncthreads();
@@ -577,6 +580,28 @@ __device__ __forceinline__ void observe_body(const DevSim& D, const SmemLayout& 
       qsum -= ob[__ldg(sc.sig_lane_off + __ldg(sc.mvo_sig + j)) + __ldg(sc.mvo_slot + j)];
     D.mplight[((size_t)env * S + sg) * 13 + 1 + mv] = qsum;
     D.wave[((size_t)env * S + sg) * 12 + mv] = wsum;
+    if (D.out_mask & RS_OUT_MPLIGHT_FULL) {   // states.mplight_full (states.py:83-113): speed = the movement's LAST lane's sum
+      float wt = 0, spd = 0, ap = 0;
+      for (int j = __ldg(sc.mv_off + x); j < __ldg(sc.mv_off + x + 1); ++j) {
+        const int q = q0 + __ldg(sc.mv_lane + j);
+        wt += ob[2 * SL + q] / 28.0f; spd = ob[4 * SL + q]; ap += ob[SL + q] / 28.0f;
+      }
+      float* mf = D.mplight_full + ((size_t)env * S + sg) * 49 + 1 + 4 * mv;
+      mf[0] = qsum; mf[1] = wt; mf[2] = spd; mf[3] = ap;
+    }
+  }
+  if (D.out_mask & (RS_OUT_DRQ | RS_OUT_DRQ_NORM)) {   // states.drq / drq_norm (states.py:6-59): the one-hot compares the LANE index with the phase
+    for (int q = tid; q < SL; q += BLOCK) {
+      const int s2 = __ldg(&sc.lane_rec[__ldg(sc.sig_lane + q)].sig);   // rs_create rejects a lane listed by two signals
+      const float oh = (q - __ldg(sc.sig_lane_off + s2)) == T.tls_phase[__ldg(sc.sig_tls + s2)] ? 1.0f : 0.0f;
+      const float queue = ob[q], appr = ob[SL + q], tw = ob[2 * SL + q], ss = ob[4 * SL + q];
+      const size_t g = ((size_t)env * SL + q) * 5;
+      if (D.out_mask & RS_OUT_DRQ) { D.drq[g] = oh; D.drq[g + 1] = appr; D.drq[g + 2] = tw; D.drq[g + 3] = queue; D.drq[g + 4] = ss; }
+      if (D.out_mask & RS_OUT_DRQ_NORM) {
+        D.drq_norm[g] = oh; D.drq_norm[g + 1] = appr / 28.0f; D.drq_norm[g + 2] = tw / 28.0f; D.drq_norm[g + 3] = queue / 28.0f;
+        D.drq_norm[g + 4] = ss / 20.0f / 28.0f;
+      }
+    }
   }
   for (int sg = tid; sg < S; sg += BLOCK) {
     int q0 = __ldg(sc.sig_lane_off + sg), q1 = __ldg(sc.sig_lane_off + sg + 1);
@@ -589,6 +614,7 @@ __device__ __forceinline__ void observe_body(const DevSim& D, const SmemLayout& 
     size_t g = (size_t)env * S + sg;
     D.phase_obs[g] = ph;
     D.mplight[g * 13] = (float)ph;
+    if (D.out_mask & RS_OUT_MPLIGHT_FULL) D.mplight_full[g * 49] = (float)ph;
     D.rew_wait[g] = -tw;
     D.rew_wait_norm[g] = fminf(fmaxf(-tw / 224.0f, -4.0f), 4.0f);
     D.rew_pressure[g] = -pr;
@@ -822,7 +848,7 @@ __global__ void k_reset(DevSim D) {
     D.origin_backlog[(size_t)env * sc.n_origins + i] = 0;
   }
   if (D.trip_rec)
-    for (int i = threadIdx.x; i < sc.n_trips; i += blockDim.x) D.trip_rec[(size_t)env * sc.n_trips + i] = make_int4(-1, 0, 0, 0);
+    for (int i = threadIdx.x; i < sc.n_trips; i += blockDim.x) { D.trip_rec[(size_t)env * sc.n_trips + i] = make_int4(-1, 0, 0, 0); D.trip_wait[(size_t)env * sc.n_trips + i] = 0.0f; }
 }
 
 __global__ void k_set_phase(DevSim D, const int32_t* phase, const uint8_t* mask) {
@@ -850,7 +876,8 @@ __global__ void k_stats(DevSim D, RsStats* out) {
   st.anomalies = h[H_ANOM]; st.sum_active_ticks = h[H_ACTIVE];
   st.sum_delay_arrived = __int_as_float(h[H_F_DELAY_ARR]);
   st.sum_duration_arrived = __int_as_float(h[H_F_DUR_ARR]);
-  st.sum_wait_arrived = 0.0f;
+  st.sum_wait_arrived = __int_as_float(h[H_F_WAIT_ARR]);
+  st.n_cap_refused = h[H_NREF];
   const uint32_t* g = D.veh + (size_t)env * kVehWords * sc.vcap;
   const float* tloss = (const float*)(g + 3 * (size_t)sc.vcap);
   const uint32_t* dl = g + 9 * (size_t)sc.vcap;
@@ -921,6 +948,7 @@ struct RsSim {
   int32_t* d_actions;
   RsStats* d_stats;
   int32_t *d_pairs, *d_valid; int n_pairs_alloc;
+  int host_obs_kind; size_t host_obs_floats;   // rs_set_host_obs
 };
 
 static thread_local std::string g_err;
@@ -999,6 +1027,14 @@ extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, ui
   if (sc->vcap <= 0 || sc->vcap % 4 || sc->vcap > 65528) return fail(RS_ERR_INVALID, "rs_create: vcap must be a positive multiple of 4 (< 65528)");
   if (sc->n_lanes >= 65535 || sc->n_signals > 254 || sc->n_routes > 65535 || sc->n_vtypes > 255)
     return fail(RS_ERR_INVALID, "rs_create: scenario exceeds the packed-field ranges");
+  {   // the per-lane sweep finds a row's signal through the lane (LaneRec::sig): one signal per inbound lane
+    std::vector<char> seen((size_t)sc->n_lanes, 0);
+    for (int q = 0; q < sc->n_sig_lanes; ++q) {
+      const int l = sc->sig_lane[q];
+      if (l < 0 || l >= sc->n_lanes || seen[l]) return fail(RS_ERR_INVALID, "rs_create: an inbound lane is listed twice in sig_lane");
+      seen[l] = 1;
+    }
+  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
     return fail(RS_ERR_NODEVICE, "rs_create: no CUDA device (this backend has no CPU fallback)");
@@ -1138,12 +1174,17 @@ extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, ui
   TRY(dev_alloc(s, s->d.wave, N * S * 12)); TRY(dev_alloc(s, s->d.rew_wait, N * S));
   TRY(dev_alloc(s, s->d.rew_wait_norm, N * S)); TRY(dev_alloc(s, s->d.rew_pressure, N * S));
   TRY(dev_alloc(s, s->d.sig_queue_len, N * S)); TRY(dev_alloc(s, s->d.sig_max_queue, N * S));
+  s->d.drq = nullptr; s->d.drq_norm = nullptr; s->d.mplight_full = nullptr; s->d.out_mask = 0;   // allocated by rs_select_outputs
+  s->d.trip_wait = nullptr;
   TRY(dev_alloc(s, s->d_actions, N * (S ? S : 1)));
   TRY(dev_alloc(s, s->d_stats, N));
   s->d.trip_rec = nullptr;
-  if (sc->record_trips && !sc->synthetic && sc->n_trips > 0) TRY(dev_alloc(s, s->d.trip_rec, N * (size_t)sc->n_trips));
+  if (sc->record_trips && !sc->synthetic && sc->n_trips > 0) {
+    TRY(dev_alloc(s, s->d.trip_rec, N * (size_t)sc->n_trips)); TRY(dev_alloc(s, s->d.trip_wait, N * (size_t)sc->n_trips));
+  }
   CK(cudaMallocHost((void**)&s->h_act_pinned, sizeof(int32_t) * N * (S ? S : 1)));
-  CK(cudaMallocHost((void**)&s->h_obs_pinned, sizeof(float) * N * (S ? S : 1) * 13));
+  s->host_obs_kind = RS_HOSTOBS_MPLIGHT; s->host_obs_floats = (size_t)(S ? S : 1) * 13;
+  CK(cudaMallocHost((void**)&s->h_obs_pinned, sizeof(float) * N * s->host_obs_floats));
   CK(cudaMallocHost((void**)&s->h_rew_pinned, sizeof(float) * N * (S ? S : 1)));
   const char* eb = getenv("RESCO_B200_BLOCK");
   const char* er = getenv("RESCO_B200_REGCAP");
@@ -1290,7 +1331,11 @@ extern "C" int rs_env_step_host_async(RsSim* s, const int32_t* h_actions, float*
   int r = rs_env_step(s, s->d_actions, st);
   if (r) return r;
   const float* rew = reward_kind == 0 ? s->d.rew_wait : (reward_kind == 1 ? s->d.rew_wait_norm : s->d.rew_pressure);
-  if (h_obs) CK(cudaMemcpyAsync(po ? h_obs : s->h_obs_pinned, s->d.mplight, sizeof(float) * NS * 13, cudaMemcpyDeviceToHost, st));
+  const size_t obs_bytes = sizeof(float) * (size_t)s->d.n_env * s->host_obs_floats;
+  const float* obs_src = s->host_obs_kind == RS_HOSTOBS_WAVE ? s->d.wave : s->host_obs_kind == RS_HOSTOBS_DRQ_NORM ? s->d.drq_norm
+                       : s->host_obs_kind == RS_HOSTOBS_DRQ ? s->d.drq : s->host_obs_kind == RS_HOSTOBS_MPLIGHT_FULL ? s->d.mplight_full
+                       : s->d.mplight;
+  if (h_obs) CK(cudaMemcpyAsync(po ? h_obs : s->h_obs_pinned, obs_src, obs_bytes, cudaMemcpyDeviceToHost, st));
   if (h_reward) CK(cudaMemcpyAsync(pr ? h_reward : s->h_rew_pinned, rew, sizeof(float) * NS, cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(s->ev_done, st));
   s->pending = true;
@@ -1305,7 +1350,7 @@ extern "C" int rs_wait(RsSim* s) {
   s->pending = false;
   CK(cudaEventSynchronize(s->ev_done));
   const size_t NS = (size_t)s->d.n_env * s->d.sc.n_signals;
-  if (s->pend_obs) memcpy(s->pend_obs, s->h_obs_pinned, sizeof(float) * NS * 13);
+  if (s->pend_obs) memcpy(s->pend_obs, s->h_obs_pinned, sizeof(float) * (size_t)s->d.n_env * s->host_obs_floats);
   if (s->pend_rew) memcpy(s->pend_rew, s->h_rew_pinned, sizeof(float) * NS);
   return 0;
 }
@@ -1369,6 +1414,7 @@ extern "C" int rs_get_obs(RsSim* s, RsObsView* o) {
   o->mplight = s->d.mplight; o->wave = s->d.wave; o->reward_wait = s->d.rew_wait;
   o->reward_wait_norm = s->d.rew_wait_norm; o->reward_pressure = s->d.rew_pressure;
   o->sig_queue_len = s->d.sig_queue_len; o->sig_max_queue = s->d.sig_max_queue; o->lane_arrivals = s->d.lane_arrivals;
+  o->drq = s->d.drq; o->drq_norm = s->d.drq_norm; o->mplight_full = s->d.mplight_full;
   return 0;
 }
 
@@ -1385,7 +1431,7 @@ extern "C" int rs_get_stats(RsSim* s, RsStats* h_out) {
 
 extern "C" int rs_dump_vehicles(RsSim* s, int32_t env, int32_t* n_out, int32_t* lane, float* pos, float* speed,
                                 float* accel, float* wait, float* rwait, float* tloss, int32_t* vid, int32_t* vtype,
-                                int32_t* route, int32_t* cursor, float* sf, int32_t* depart) {
+                                int32_t* route, int32_t* cursor, float* sf, int32_t* depart, float* acc_wait) {
   if (!s || env < 0 || env >= s->d.n_env || !n_out) return fail(RS_ERR_INVALID, "rs_dump_vehicles: bad arguments");
   CK(cudaSetDevice(s->device));
   CK(cudaDeviceSynchronize());
@@ -1398,7 +1444,7 @@ extern "C" int rs_dump_vehicles(RsSim* s, int32_t env, int32_t* n_out, int32_t* 
   const float* fpos = (const float*)&buf[0]; const float* fspeed = (const float*)&buf[(size_t)vcap];
   const float* fsf = (const float*)&buf[2 * (size_t)vcap]; const float* ftl = (const float*)&buf[3 * (size_t)vcap];
   const uint32_t *wvid = &buf[4 * (size_t)vcap], *wr = &buf[5 * (size_t)vcap], *rc = &buf[6 * (size_t)vcap];
-  const uint32_t *mt = &buf[7 * (size_t)vcap], *ed = &buf[8 * (size_t)vcap], *dl = &buf[9 * (size_t)vcap];
+  const uint32_t *mt = &buf[7 * (size_t)vcap], *ed = &buf[8 * (size_t)vcap], *dl = &buf[9 * (size_t)vcap], *aw = &buf[10 * (size_t)vcap];
   for (int i = 0; i < n; ++i) {
     if (lane) lane[i] = (int32_t)(dl[i] >> 16);
     if (pos) pos[i] = fpos[i];
@@ -1413,6 +1459,7 @@ extern "C" int rs_dump_vehicles(RsSim* s, int32_t env, int32_t* n_out, int32_t* 
     if (cursor) cursor[i] = (int32_t)(rc[i] >> 16);
     if (sf) sf[i] = fsf[i];
     if (depart) depart[i] = (int32_t)(ed[i] >> 16);
+    if (acc_wait) acc_wait[i] = (float)(aw[i] & 0xFFFFu);
   }
   *n_out = n;
   return 0;
@@ -1428,7 +1475,7 @@ extern "C" int rs_get_phases(RsSim* s, int32_t env, int32_t* h_tls_phase) {
 }
 
 extern "C" int rs_get_trip_records(RsSim* s, int32_t env, int32_t* h_arrival_tick, int32_t* h_depart_tick,
-                                   float* h_time_loss, int32_t* h_depart_delay) {
+                                   float* h_time_loss, int32_t* h_depart_delay, float* h_waiting_time) {
   if (!s || env < 0 || env >= s->d.n_env) return fail(RS_ERR_INVALID, "rs_get_trip_records: bad arguments");
   if (!s->d.trip_rec) return fail(RS_ERR_INVALID, "rs_get_trip_records: RsScenario.record_trips was not set");
   CK(cudaSetDevice(s->device));
@@ -1442,6 +1489,35 @@ extern "C" int rs_get_trip_records(RsSim* s, int32_t env, int32_t* h_arrival_tic
     if (h_time_loss) memcpy(&h_time_loss[i], &buf[i].z, 4);
     if (h_depart_delay) h_depart_delay[i] = buf[i].w;
   }
+  if (h_waiting_time) CK(cudaMemcpy(h_waiting_time, s->d.trip_wait + (size_t)env * n, sizeof(float) * n, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int rs_select_outputs(RsSim* s, int32_t mask) {
+  if (!s || (mask & ~(RS_OUT_DRQ | RS_OUT_DRQ_NORM | RS_OUT_MPLIGHT_FULL))) return fail(RS_ERR_INVALID, "rs_select_outputs: bad arguments");
+  CK(cudaSetDevice(s->device));
+  const size_t N = (size_t)s->d.n_env, SL = (size_t)s->d.sc.n_sig_lanes, S = (size_t)s->d.sc.n_signals;
+  if ((mask & RS_OUT_DRQ) && !s->d.drq) TRY(dev_alloc(s, s->d.drq, N * SL * 5));
+  if ((mask & RS_OUT_DRQ_NORM) && !s->d.drq_norm) TRY(dev_alloc(s, s->d.drq_norm, N * SL * 5));
+  if ((mask & RS_OUT_MPLIGHT_FULL) && !s->d.mplight_full) TRY(dev_alloc(s, s->d.mplight_full, N * S * 49));
+  s->d.out_mask = mask;
+  return 0;
+}
+
+extern "C" int rs_set_host_obs(RsSim* s, int32_t kind, int32_t* floats_per_instance) {
+  if (!s || kind < RS_HOSTOBS_MPLIGHT || kind > RS_HOSTOBS_MPLIGHT_FULL) return fail(RS_ERR_INVALID, "rs_set_host_obs: bad arguments");
+  if (s->pending) return fail(RS_ERR_INVALID, "rs_set_host_obs: a step is pending (call rs_wait)");
+  const size_t SL = (size_t)s->d.sc.n_sig_lanes, S = (size_t)s->d.sc.n_signals;
+  const size_t fl = kind == RS_HOSTOBS_MPLIGHT ? S * 13 : kind == RS_HOSTOBS_WAVE ? S * 12 : kind == RS_HOSTOBS_MPLIGHT_FULL ? S * 49 : SL * 5;
+  const int need = kind == RS_HOSTOBS_DRQ_NORM ? RS_OUT_DRQ_NORM : kind == RS_HOSTOBS_DRQ ? RS_OUT_DRQ : kind == RS_HOSTOBS_MPLIGHT_FULL ? RS_OUT_MPLIGHT_FULL : 0;
+  if (need) TRY(rs_select_outputs(s, s->d.out_mask | need));
+  if (fl > s->host_obs_floats) {   // the staging buffer for pageable callers grows with the row size
+    if (s->h_obs_pinned) cudaFreeHost(s->h_obs_pinned);
+    s->h_obs_pinned = nullptr;
+    CK(cudaMallocHost((void**)&s->h_obs_pinned, sizeof(float) * (size_t)s->d.n_env * (fl ? fl : 1)));
+  }
+  s->host_obs_kind = kind; s->host_obs_floats = fl ? fl : 1;
+  if (floats_per_instance) *floats_per_instance = (int32_t)fl;
   return 0;
 }
 

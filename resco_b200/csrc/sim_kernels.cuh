@@ -34,12 +34,12 @@ constexpr float kNumEps = 0.001f;
 constexpr float kEmergencyDecel = 9.0f;
 constexpr int kLcCooldown = 5;
 constexpr float kCoopMargin = 1.0f;   // extra room a yielding follower leaves behind an urgent lane changer (oracle: COOP_MARGIN)
-constexpr int kVehWords = 10;      // 32-bit words per vehicle record
+constexpr int kVehWords = 11;      // 32-bit words per vehicle record
 constexpr int kHdrInts = 16;
 constexpr uint32_t kArrived = 0xFFFFu;
 
 // header slots (ints; floats bit-cast)
-enum { H_TICK = 0, H_NVEH, H_EPOCH, H_NINS, H_NARR, H_ANOM, H_ACTIVE, H_F_DELAY_ARR, H_F_DUR_ARR, H_F_PENDING };
+enum { H_TICK = 0, H_NVEH, H_EPOCH, H_NINS, H_NARR, H_ANOM, H_ACTIVE, H_F_DELAY_ARR, H_F_DUR_ARR, H_F_PENDING, H_NREF, H_F_WAIT_ARR };
 
 // vtype table columns
 enum { VT_LEN = 0, VT_GAP, VT_ACCEL, VT_DECEL, VT_TAU, VT_SIGMA, VT_VMAX, VT_DEV };
@@ -97,6 +97,10 @@ struct DevSim {
   float *mplight, *wave, *rew_wait, *rew_wait_norm, *rew_pressure;
   int32_t *sig_queue_len, *sig_max_queue;
   int4* trip_rec;         // [N][n_trips] {arrival tick, depart tick, timeLoss bits, depart delay} or null
+  float* trip_wait;       // [N][n_trips] tripinfo waitingTime (with trip_rec)
+  float *drq, *drq_norm;  // [N][SL][5] optional (out_mask)
+  float* mplight_full;    // [N][S][49] optional
+  int32_t out_mask;       // RS_OUT_* bits
   int32_t* work_counter;  // dynamic instance scheduler of the persistent launch
   unsigned long long* phase_clocks;   // [24] diagnostics (RS_PHASE_CLOCKS builds)
   int32_t persistent;
@@ -177,6 +181,7 @@ struct Tile {
   uint32_t* meta;  // vtype (8) | lcc (8) | seen_sig (8, 0xFF none) | spare
   uint32_t* ed;    // seen_epoch (lo16) | depart tick (hi16)
   uint32_t* dl;    // depart delay (lo16) | lane (hi16)
+  uint32_t* aw;    // accumulated waiting seconds, the tripinfo waitingTime (lo16) | spare (hi16)
   uint16_t* lane_start;   // [L+1]
   const uint32_t* occ;    // [(L+31)/32 + 2] bit l = lane l holds a vehicle (state at the start of the tick)
   int32_t* tls_phase; int32_t* tls_end;
@@ -190,6 +195,7 @@ __device__ __forceinline__ void tile_bind(Tile& t, uint32_t* base, int vcap) {
   t.pos = (float*)(base + 0 * vcap); t.speed = (float*)(base + 1 * vcap); t.sf = (float*)(base + 2 * vcap);
   t.tloss = (float*)(base + 3 * vcap); t.vid = (int32_t*)(base + 4 * vcap); t.wr = base + 5 * vcap;
   t.rc = base + 6 * vcap; t.meta = base + 7 * vcap; t.ed = base + 8 * vcap; t.dl = base + 9 * vcap;
+  t.aw = base + 10 * vcap;
 }
 
 // re-point the view at the tile of another instance slot of the same CTA (`delta` bytes away in shared memory); all
@@ -200,7 +206,7 @@ template <typename P> __device__ __forceinline__ void ptr_shift(P*& p, ptrdiff_t
 __device__ __forceinline__ void tile_shift(Tile& t, ptrdiff_t delta) {
   ptr_shift(t.pos, delta); ptr_shift(t.speed, delta); ptr_shift(t.sf, delta); ptr_shift(t.tloss, delta);
   ptr_shift(t.vid, delta); ptr_shift(t.wr, delta); ptr_shift(t.rc, delta); ptr_shift(t.meta, delta);
-  ptr_shift(t.ed, delta); ptr_shift(t.dl, delta); ptr_shift(t.lane_start, delta); ptr_shift(t.tls_phase, delta);
+  ptr_shift(t.ed, delta); ptr_shift(t.dl, delta); ptr_shift(t.aw, delta); ptr_shift(t.lane_start, delta); ptr_shift(t.tls_phase, delta);
   ptr_shift(t.tls_end, delta); ptr_shift(t.tls_state, delta); ptr_shift(t.occ, delta); ptr_shift(t.vt, delta);
 }
 

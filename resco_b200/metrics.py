@@ -34,7 +34,7 @@ def write_tripinfo(path: str, scenario, records: Dict[str, np.ndarray], running:
             arr = begin + float(records["arrival"][i])
             f.write(f'    <tripinfo id="{ids[i]}" depart="{dep:.2f}" departDelay="{float(records["depart_delay"][i]):.2f}" '
                     f'arrival="{arr:.2f}" duration="{arr - dep:.2f}" timeLoss="{float(records["time_loss"][i]):.2f}" '
-                    f'waitingTime="0.00" vType="{vt_ids[int(vt_of[i])]}"/>\n')
+                    f'waitingTime="{float(records["waiting_time"][i]):.2f}" vType="{vt_ids[int(vt_of[i])]}"/>\n')
             n += 1
         for k in range(len(running["vid"])):          # --tripinfo-output.write-unfinished
             i = int(running["vid"][k])
@@ -42,7 +42,7 @@ def write_tripinfo(path: str, scenario, records: Dict[str, np.ndarray], running:
             ddelay = float(running["depart"][k]) - float(scenario.arrays["trip_depart"][i])
             f.write(f'    <tripinfo id="{ids[i]}" depart="{dep:.2f}" departDelay="{ddelay:.2f}" arrival="-1.00" '
                     f'duration="{begin + now_tick - dep:.2f}" timeLoss="{float(running["tloss"][k]):.2f}" '
-                    f'waitingTime="0.00" vType="{vt_ids[int(vt_of[i])]}"/>\n')
+                    f'waitingTime="{float(running["acc_wait"][k]):.2f}" vType="{vt_ids[int(vt_of[i])]}"/>\n')
             n += 1
         f.write('</tripinfos>\n')
     return n

@@ -100,6 +100,9 @@ class MultiSignal(_EnvBase):
                                   sigma=sigma, speed_dev=speed_dev, record_trips=self.tripinfo)
         m = self.marshalled
         self.sim = (backend or _default_backend(self.n_env, device))(m)
+        outs = tuple(getattr(state_fn, 'kernel_outputs', ())) + tuple(getattr(reward_fn, 'kernel_outputs', ()))
+        if outs and hasattr(self.sim, 'select_outputs'):
+            self.sim.select_outputs(*outs)
         self._begin = float(sc.meta["begin"])
         self._end_tick = m.struct.end_tick
         self._tick = 0
@@ -121,6 +124,7 @@ class MultiSignal(_EnvBase):
         self._episode_seed = 0 if seed is None else int(seed)
         self.sim.reset(self._episode_seed, 0)
         self.sim.observe()
+        self._observed_tick = 0
         self._refresh_views()
         self.obs_shape = dict()
         self.observation_space = list()
@@ -212,8 +216,14 @@ class MultiSignal(_EnvBase):
         self._phases = self.sim.phases(0)[self.scenario.arrays["sig_tls"]]
 
     def _observe_into_signals(self):
-        self.sim.observe()
-        self._refresh_views()
+        """Signal.observe() of a caller that drives the signals by hand (N = 1): the reference loops
+        ``for ts in signal_ids: signals[ts].observe(...)`` (multi_signal.py:185-186) and every call latches only ITS
+        signal's waiting times.  The device sweep covers all signals at once, so it runs once per tick: the first
+        Signal.observe() after a tick does the sweep, the calls for the other signals in the same tick find it done."""
+        if getattr(self, '_observed_tick', None) != self._tick:
+            self.sim.observe()
+            self._observed_tick = self._tick
+            self._refresh_views()
 
     def _refresh_views(self, env: int = 0):
         """Per-instance dict view (Signal.full_observation) of instance `env` from the device buffers."""
@@ -289,6 +299,7 @@ class MultiSignal(_EnvBase):
         self.signal_ids = list(self.all_ts_ids)
         self._make_signals()
         self.sim.observe()
+        self._observed_tick = 0
         if self.n_env > 1:
             self._n_prev = None
             self._n_now = self._count_present()
@@ -314,6 +325,7 @@ class MultiSignal(_EnvBase):
             a[0, i] = int(act[ts])
         self.sim.env_step(a)                  # prep_phase -> yellow ticks -> set_phase -> green ticks -> observe
         self._tick += self.step_length
+        self._observed_tick = self._tick
         self._refresh_views()
         observations = self.state_fn(self.signals)
         rewards = self.reward_fn(self.signals)

@@ -33,6 +33,64 @@ def pressure(signals):
     return out
 
 
+def _ma2c_cfg(signals):
+    """mdp_configs['MA2C'] (rewards.py:51,66).  The reference ships no 'MA2C' entry in config/mdp_config.py, so its
+    queue_maxwait* raise KeyError unless the caller has put one there (main.py:48-53 does for the agent it runs); same
+    here: the entry is looked up in the scenario's mdp table (``env.scenario.meta['mdp']['MA2C']``: coef, coop_gamma)."""
+    env = next(iter(signals.values()))._env
+    return env.scenario.meta.get('mdp', {})['MA2C']
+
+
+def queue_maxwait(signals):
+    """rewards.py:44-53 -- -(sum over lanes of queue + coef * max_wait)."""
+    coef = _ma2c_cfg(signals)['coef']
+    out = dict()
+    for sid, sig in signals.items():
+        r = 0
+        for lane in sig.lanes:
+            r += sig.full_observation[lane]['queue']
+            r += sig.full_observation[lane]['max_wait'] * coef
+        out[sid] = -r
+    return out
+
+
+def queue_maxwait_neighborhood(signals):
+    """rewards.py:56-69 -- own queue_maxwait + coop_gamma x that of every downstream neighbour."""
+    own = queue_maxwait(signals)
+    gamma = _ma2c_cfg(signals)['coop_gamma']
+    out = dict()
+    for sid, sig in signals.items():
+        tot = own[sid]
+        for neighbor in sig.downstream.values():
+            if neighbor is not None:
+                tot += gamma * own[neighbor]
+        out[sid] = tot
+    return out
+
+
+def _b_queue_maxwait(env, neighborhood):
+    """[N, S] device tensor from the kernel's per-lane queue / max_wait rows."""
+    import torch
+    cfg = env.scenario.meta.get('mdp', {})['MA2C']
+    v = env.sim.obs_view()
+    dev = v["lane_queue"].device
+    cache = env.__dict__.setdefault('_ma2c_plan', None)
+    if cache is None:
+        S, SL = len(env.signal_ids), env.sim.SL
+        lane_to_sig = torch.zeros((SL, S), device=dev)
+        nb = torch.zeros((S, S), device=dev)
+        for si, sid in enumerate(env.signal_ids):
+            lane_to_sig[env.sig_lane_slices[si], si] = 1.0
+            nb[si, si] += 1.0
+            for neighbor in env.signals[sid].downstream.values():
+                if neighbor is not None:
+                    nb[env.signal_ids.index(neighbor), si] += float(cfg['coop_gamma'])
+        cache = env.__dict__['_ma2c_plan'] = (lane_to_sig, nb)
+    lane_to_sig, nb = cache
+    own = -((v["lane_queue"] + v["lane_max_wait"] * float(cfg['coef'])) @ lane_to_sig)
+    return own @ nb if neighborhood else own
+
+
 def _fma2c(signals, key):
     from .states import _mdp, _region_fringes
     cfg = _mdp(signals, key)
@@ -138,6 +196,8 @@ def _b_fma2c(env, key):
 
 fma2c.batched = lambda env: _b_fma2c(env, 'FMA2C')
 fma2c_full.batched = lambda env: _b_fma2c(env, 'FMA2CFull')
+queue_maxwait.batched = lambda env: _b_queue_maxwait(env, False)
+queue_maxwait_neighborhood.batched = lambda env: _b_queue_maxwait(env, True)
 wait.batched = lambda env: env.sim.obs_view()["reward_wait"]
 wait_norm.batched = lambda env: env.sim.obs_view()["reward_wait_norm"]
 pressure.batched = lambda env: env.sim.obs_view()["reward_pressure"]

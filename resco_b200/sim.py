@@ -14,7 +14,7 @@ from typing import Dict, Optional
 
 import numpy as np
 
-from .abi import Marshalled, RsObsView, RsScenario, RsStats, STATS_DTYPE
+from .abi import HOSTOBS, Marshalled, RsObsView, RsScenario, RsStats, STATS_DTYPE
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
@@ -39,7 +39,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
 EXPORTS = ["rs_last_error", "rs_abi_version", "rs_create", "rs_destroy", "rs_reset", "rs_set_phase", "rs_tick",
            "rs_observe", "rs_env_step", "rs_env_step_host", "rs_env_step_host_async", "rs_wait", "rs_policy_maxpressure", "rs_host_agent_wave", "rs_get_obs", "rs_get_stats",
-           "rs_dump_vehicles", "rs_get_phases", "rs_get_trip_records", "rs_kernel_launches", "rs_last_step_ms", "rs_get_launch_shape"]
+           "rs_dump_vehicles", "rs_get_phases", "rs_get_trip_records", "rs_kernel_launches", "rs_last_step_ms", "rs_get_launch_shape",
+           "rs_select_outputs", "rs_set_host_obs"]
 
 
 def load_library():
@@ -69,9 +70,11 @@ def load_library():
                                        C.c_void_p, C.c_void_p]
     lib.rs_get_obs.argtypes = [C.c_void_p, C.POINTER(RsObsView)]
     lib.rs_get_stats.argtypes = [C.c_void_p, C.c_void_p]
-    lib.rs_dump_vehicles.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32)] + [C.c_void_p] * 13
+    lib.rs_dump_vehicles.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32)] + [C.c_void_p] * 14
     lib.rs_get_phases.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
-    lib.rs_get_trip_records.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 4
+    lib.rs_get_trip_records.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 5
+    lib.rs_select_outputs.argtypes = [C.c_void_p, C.c_int32]
+    lib.rs_set_host_obs.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
     lib.rs_kernel_launches.restype = C.c_int64
     lib.rs_kernel_launches.argtypes = [C.c_void_p]
     lib.rs_last_step_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
@@ -92,13 +95,15 @@ def _check(lib, rc: int):
 _VEH_FIELDS = [("lane", np.int32), ("pos", np.float32), ("speed", np.float32), ("accel", np.float32),
                ("wait", np.float32), ("rwait", np.float32), ("tloss", np.float32), ("vid", np.int32),
                ("vtype", np.int32), ("route", np.int32), ("cursor", np.int32), ("sf", np.float32),
-               ("depart", np.int32)]
+               ("depart", np.int32), ("acc_wait", np.float32)]
 
 _OBS_FIELDS = [("lane_queue", "f", "L"), ("lane_approach", "f", "L"), ("lane_total_wait", "f", "L"),
                ("lane_max_wait", "f", "L"), ("lane_speed_sum", "f", "L"), ("phase", "i", "S"),
                ("mplight", "f", "S13"), ("wave", "f", "S12"), ("reward_wait", "f", "S"),
                ("reward_wait_norm", "f", "S"), ("reward_pressure", "f", "S"), ("sig_queue_len", "i", "S"),
-               ("sig_max_queue", "i", "S"), ("lane_arrivals", "f", "L")]
+               ("sig_max_queue", "i", "S"), ("lane_arrivals", "f", "L"),
+               ("drq", "f", "L5"), ("drq_norm", "f", "L5"), ("mplight_full", "f", "S49")]
+_OPTIONAL_OUT = {"drq": 1, "drq_norm": 2, "mplight_full": 4}          # RS_OUT_* bit of the optional tensors
 
 
 def policy_tables(pairs, valid_acts, signal_ids):
@@ -208,11 +213,33 @@ class VecSim:
         self._keep_actions = actions
         _check(self.lib, self.lib.rs_env_step(self._h, actions.data_ptr(), self._stream()))
 
+    def select_outputs(self, *names: str):
+        """Switch on optional observation tensors ("drq", "drq_norm", "mplight_full"); cumulative."""
+        mask = getattr(self, "_out_mask", 0)
+        for n in names:
+            mask |= _OPTIONAL_OUT[n]
+        _check(self.lib, self.lib.rs_select_outputs(self._h, mask))
+        self._out_mask = mask
+        self._views = None
+
+    def set_host_obs(self, kind: str = "mplight"):
+        """Choose the tensor env_step_host / env_step_host_async return as observation: "mplight" [N, S, 13],
+        "wave" [N, S, 12], "drq_norm" / "drq" [N, n_sig_lanes, 5], "mplight_full" [N, S, 49]."""
+        fl = C.c_int32(0)
+        _check(self.lib, self.lib.rs_set_host_obs(self._h, HOSTOBS[kind], C.byref(fl)))
+        if kind in _OPTIONAL_OUT:
+            self._out_mask = getattr(self, "_out_mask", 0) | _OPTIONAL_OUT[kind]
+        self._host_obs_shape = {"mplight": (self.n_env, self.S, 13), "wave": (self.n_env, self.S, 12),
+                                "mplight_full": (self.n_env, self.S, 49)}.get(kind, (self.n_env, self.SL, 5))
+        self._host_bufs = None
+        self._views = None
+
     def _host_buffers(self):
         if getattr(self, "_host_bufs", None) is None:
             t = self._torch
+            shape = getattr(self, "_host_obs_shape", (self.n_env, self.S, 13))
             self._host_bufs = (t.empty((self.n_env, self.S), dtype=t.int32).pin_memory(),
-                               t.empty((self.n_env, self.S, 13), dtype=t.float32).pin_memory(),
+                               t.empty(shape, dtype=t.float32).pin_memory(),
                                t.empty((self.n_env, self.S), dtype=t.float32).pin_memory())
             self._host_np = tuple(b.numpy() for b in self._host_bufs)
         return self._host_bufs, self._host_np
@@ -262,10 +289,12 @@ class VecSim:
             v = RsObsView()
             _check(self.lib, self.lib.rs_get_obs(self._h, C.byref(v)))
             shapes = {"L": (self.n_env, self.SL), "S": (self.n_env, self.S), "S13": (self.n_env, self.S, 13),
-                      "S12": (self.n_env, self.S, 12)}
+                      "S12": (self.n_env, self.S, 12), "L5": (self.n_env, self.SL, 5), "S49": (self.n_env, self.S, 49)}
             out = {}
             for name, kind, shp in _OBS_FIELDS:
                 ptr = getattr(v, name)
+                if not ptr:          # optional tensor that was not selected (select_outputs)
+                    continue
                 shape = shapes[shp]
                 n = int(np.prod(shape))
                 out[name] = _wrap_device(t, ptr, n, kind, self.device).view(*shape) if n > 0 else \
@@ -297,9 +326,10 @@ class VecSim:
     def trip_records(self, env: int = 0) -> Dict[str, np.ndarray]:
         n = self.m.struct.n_trips
         out = dict(arrival=np.zeros(n, np.int32), depart=np.zeros(n, np.int32), time_loss=np.zeros(n, np.float32),
-                   depart_delay=np.zeros(n, np.int32))
+                   depart_delay=np.zeros(n, np.int32), waiting_time=np.zeros(n, np.float32))
         _check(self.lib, self.lib.rs_get_trip_records(self._h, env, out["arrival"].ctypes.data, out["depart"].ctypes.data,
-                                                      out["time_loss"].ctypes.data, out["depart_delay"].ctypes.data))
+                                                      out["time_loss"].ctypes.data, out["depart_delay"].ctypes.data,
+                                                      out["waiting_time"].ctypes.data))
         return out
 
     def kernel_launches(self) -> int:

@@ -172,20 +172,13 @@ def _b_wave(env):
 
 
 def _b_drq(env, norm):
-    """[N, n_sig_lanes, 5] rows in signal-major lane order (ragged per signal: see env.sig_lane_slices)."""
-    import torch
+    """[N, n_sig_lanes, 5] rows in signal-major lane order (ragged per signal: see env.sig_lane_slices), written by the
+    observe step of the kernel (RS_OUT_DRQ / RS_OUT_DRQ_NORM, switched on by MultiSignal for these state functions)."""
+    name = "drq_norm" if norm else "drq"
     v = env.sim.obs_view()
-    SL = env.sim.SL
-    phase = v["phase"]                                       # [N, S]
-    lane_sig = env.lane_sig_t                                # [SL] signal of each row
-    lane_slot = env.lane_slot_t                              # [SL] row index inside the signal
-    onehot = (lane_slot[None, :] == phase[:, lane_sig]).to(torch.float32)
-    if norm:
-        cols = [onehot, v["lane_approach"] / 28, v["lane_total_wait"] / 28, v["lane_queue"] / 28,
-                v["lane_speed_sum"] / 20 / 28]
-    else:
-        cols = [onehot, v["lane_approach"], v["lane_total_wait"], v["lane_queue"], v["lane_speed_sum"]]
-    return torch.stack(cols, dim=-1).view(-1, SL, 5)
+    if name not in v:
+        raise RuntimeError(f"states.{name}.batched: the '{name}' output is not selected (VecSim.select_outputs)")
+    return v[name]
 
 
 def _lane_rows(env):
@@ -260,34 +253,13 @@ def _b_fma2c(env, key, full):
 
 
 def _b_mplight_full(env):
-    """[N, S, 1 + 48] device tensor: phase, then per movement (pressure, sum(total_wait)/28, speed sum of the LAST lane
-    of the movement -- the reference resets total_speed inside its lane loop, states.py:97 --, sum(approach)/28)."""
-    import torch
+    """[N, S, 1 + 48] device tensor written by the kernel (RS_OUT_MPLIGHT_FULL): phase, then per movement (pressure,
+    sum(total_wait / 28), speed sum of the LAST lane of the movement -- the reference resets total_speed inside its
+    lane loop, states.py:97 --, sum(approach / 28))."""
     v = env.sim.obs_view()
-    dev = v["lane_queue"].device
-    plan = env.__dict__.get('_mplight_full_plan')
-    if plan is None:
-        S, SL = len(env.signal_ids), env.sim.SL
-        lanes_to_mv = torch.zeros((SL, S * 12), device=dev)
-        last = torch.zeros((SL, S * 12), device=dev)
-        for si, sid in enumerate(env.signal_ids):
-            sig = env.signals[sid]
-            q0 = env.sig_lane_slices[si].start
-            for mi, d in enumerate(sig.lane_sets):
-                rows = [q0 + sig.lanes.index(lane) for lane in sig.lane_sets[d]]
-                for q in rows:
-                    lanes_to_mv[q, si * 12 + mi] += 1.0
-                if rows:
-                    last[rows[-1], si * 12 + mi] = 1.0
-        plan = env.__dict__['_mplight_full_plan'] = (lanes_to_mv, last)
-    lanes_to_mv, last = plan
-    N, S = v["phase"].shape
-    mp = v["mplight"]
-    wait = ((v["lane_total_wait"] / 28) @ lanes_to_mv).view(N, S, 12)
-    speed = (v["lane_speed_sum"] @ last).view(N, S, 12)
-    appr = ((v["lane_approach"] / 28) @ lanes_to_mv).view(N, S, 12)
-    per_mv = torch.stack([mp[:, :, 1:], wait, speed, appr], dim=-1).reshape(N, S, 48)
-    return torch.cat([mp[:, :, :1], per_mv], dim=-1)
+    if "mplight_full" not in v:
+        raise RuntimeError("states.mplight_full.batched: the 'mplight_full' output is not selected (VecSim.select_outputs)")
+    return v["mplight_full"]
 
 
 mplight.batched = _b_mplight
@@ -297,3 +269,7 @@ fma2c.batched = lambda env: _b_fma2c(env, 'FMA2C', False)
 fma2c_full.batched = lambda env: _b_fma2c(env, 'FMA2CFull', True)
 drq.batched = lambda env: _b_drq(env, False)
 drq_norm.batched = lambda env: _b_drq(env, True)
+# optional kernel outputs a state function needs (MultiSignal switches them on: VecSim.select_outputs)
+drq.kernel_outputs = ("drq",)
+drq_norm.kernel_outputs = ("drq_norm",)
+mplight_full.kernel_outputs = ("mplight_full",)

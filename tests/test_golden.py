@@ -22,12 +22,12 @@ def _oracle_backend(m):
     return OracleSim(m, 1, seed=0)
 
 
-def _run_case(path, backend):
+def _run_case(path, backend, vcap=0):
     z = np.load(path)
     meta = json.loads(bytes(z["meta"]).decode())
     env = MultiSignal("golden", meta["map"], None, getattr(states, meta["state"]), getattr(rewards, meta["reward"]),
                       step_length=meta["step_length"], yellow_length=meta["yellow_length"],
-                      max_distance=meta["max_distance"], log_dir=None, backend=backend)
+                      max_distance=meta["max_distance"], log_dir=None, backend=backend, vcap=vcap)
     order = meta["ts_order"]
     assert env.ts_order == order
     assert {ts: list(env.obs_shape[ts]) for ts in order} == meta["obs_shapes"]
@@ -64,6 +64,16 @@ def test_reference_golden_cpu(path):
 @pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
 def test_reference_golden_gpu(path):
     _run_case(path, None)      # default backend = CUDA VecSim through the C-ABI
+
+
+GOLD_C8 = [p for p in GOLD if os.path.basename(p).startswith("cologne8_")]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GOLD_C8, ids=[os.path.basename(p)[:-4] for p in GOLD_C8])
+def test_reference_golden_gpu_bench_tile(path):
+    """the cologne8 goldens again on the 128-vehicle tile bench.py times (launch shape k_run<64, 8, 1>)"""
+    _run_case(path, None, vcap=128)
 
 
 def test_goldens_present():

@@ -17,16 +17,23 @@ def _pair(map_name, n_env, **kw):
     from resco_b200.sim import VecSim
     sc, m = util.marshal_map(map_name, **kw)
     g = VecSim(m, n_env, seed=7)
+    g.select_outputs("drq", "drq_norm", "mplight_full")       # optional state tensors: compared by assert_same_obs
     o = OracleSim(m, n_env, seed=7)
     g.reset(7, 0)
     o.reset(7, 0)
     return sc, m, g, o
 
 
-@pytest.mark.parametrize("map_name,n_env,steps", [("cologne1", 3, 120), ("cologne8", 4, 120), ("grid4x4", 2, 90),
-                                                   ("ingolstadt21", 2, 60), ("cologne3", 2, 60)])
-def test_env_step_parity_cyclic(map_name, n_env, steps):
-    sc, m, g, o = _pair(map_name, n_env)
+@pytest.mark.parametrize("map_name,n_env,steps,vcap", [("cologne1", 3, 120, 0), ("cologne8", 4, 120, 0), ("grid4x4", 2, 90, 0),
+                                                        ("ingolstadt21", 2, 60, 0), ("cologne3", 2, 60, 0),
+                                                        # the launch shape bench.py times (C2): vcap 128 -> k_run<64, 8, 1>,
+                                                        # 19 instances = two full groups of 8 and a ragged one
+                                                        ("cologne8", 19, 120, 128)])
+def test_env_step_parity_cyclic(map_name, n_env, steps, vcap):
+    sc, m, g, o = _pair(map_name, n_env, vcap=vcap)
+    if vcap == 128:
+        shape = g.launch_shape()
+        assert (shape["threads_per_instance"], shape["instances_per_cta"]) == (64, 8), shape
     g.observe(); o.observe()
     util.assert_same_obs(g.obs(), o.obs(), "reset observe")
     for step in range(steps):
@@ -37,16 +44,15 @@ def test_env_step_parity_cyclic(map_name, n_env, steps):
             for e in range(n_env):
                 util.assert_same_state(g, o, e, f"{map_name} step {step} env {e}")
     sg, so = g.stats(), o.stats()
-    for k in ("tick", "n_active", "n_inserted", "n_arrived", "n_backlog", "anomalies", "sum_active_ticks"):
-        assert np.array_equal(sg[k], so[k]), k
-    for k in ("sum_delay_arrived", "sum_delay_running", "sum_delay_pending", "sum_duration_arrived"):
-        assert np.array_equal(sg[k], so[k]), (k, sg[k], so[k])
-    assert (sg["anomalies"] == 0).all()
+    util.assert_same_stats(sg, so, map_name)
+    assert (sg["anomalies"] == 0).all() and (sg["n_cap_refused"] == 0).all()
 
 
-def test_full_episode_maxpressure_cologne8():
-    """BASELINE config C2 shape (cologne8 / MaxPressure), whole 360-step episode, 2 instances."""
-    sc, m, g, o = _pair("cologne8", 2)
+@pytest.mark.parametrize("vcap,n_env", [(0, 2), (128, 9)])
+def test_full_episode_maxpressure_cologne8(vcap, n_env):
+    """BASELINE config C2 (cologne8 / MaxPressure), whole 360-step episode; vcap 128 is the tile bench.py times
+    (k_run<64, 8, 1>: nine instances = one full group of eight and a ragged one)."""
+    sc, m, g, o = _pair("cologne8", n_env, vcap=vcap)
     g.observe(); o.observe()
     nsteps = m.struct.end_tick // m.struct.step_length
     for step in range(nsteps):
@@ -57,12 +63,13 @@ def test_full_episode_maxpressure_cologne8():
         dev_act = g.policy_maxpressure(sc.meta["phase_pairs"], sc.meta["valid_acts"], m.info["signal_ids"]).cpu().numpy()
         assert np.array_equal(dev_act, act), f"device MaxPressure differs at step {step}"
         g.env_step(act); o.env_step(act)
-    util.assert_same_state(g, o, 0, "end")
+    for e in range(n_env):
+        util.assert_same_state(g, o, e, f"end env {e}")
     sg, so = g.stats(), o.stats()
-    assert np.array_equal(sg["n_arrived"], so["n_arrived"])
-    assert np.array_equal(sg["sum_delay_arrived"], so["sum_delay_arrived"])
-    n = sg["n_arrived"] + sg["n_active"] + sg["n_backlog"]
-    delay = (sg["sum_delay_arrived"] + sg["sum_delay_running"] + sg["sum_delay_pending"]) / n
+    util.assert_same_stats(sg, so, "episode end")
+    assert (sg["n_cap_refused"] == 0).all()      # the 128-vehicle tile never refused an insertion
+    n = sg["n_arrived"] + sg["n_active"]
+    delay = (sg["sum_delay_arrived"] + sg["sum_delay_running"]) / n
     # statistical anchor (not parity): reference MAXPRESSURE cologne8 first-episode 28.76 s, mean 47.73 s
     # (MaxPressure can lock an instance into gridlock -- the reference's own runs show it, cologne1 row)
     assert 15 < delay.min() < 80, delay
@@ -158,52 +165,52 @@ def test_synthetic_grid_parity():
     assert (sg["n_backlog"] > 0).any()          # demand above capacity: the backlog path is exercised
 
 
-def test_full_size_batch_properties():
-    """BASELINE configs[1] at FULL size (cologne8 / MaxPressure / 4096 lock-step instances): size-independent
-    properties + oracle spot checks.  (a) vehicle conservation and zero ordering anomalies in every instance,
-    (b) instances are independent and keyed by their global id: instance i of the 4096-batch is bit-identical to
-    the oracle run alone with first_env_id = i under the same actions, (c) a second run reproduces the first."""
+def test_full_size_batch_all_instances():
+    """BASELINE configs[1] at FULL size (cologne8 / MaxPressure / 4096 lock-step instances, the 128-vehicle tile and the
+    launch shape bench.py times): EVERY instance against the oracle -- observations, rewards, metrics and episode
+    statistics of all 4096, per-vehicle state of a sample --, plus the size-independent properties: vehicle
+    conservation, zero ordering anomalies, zero capacity refusals, instances keyed by their global id (the oracle runs
+    them in a different grouping), and a second run reproducing the first bit for bit."""
     from pyoracle import OracleSim
     from resco_b200.sim import VecSim
     sc, m = util.marshal_map("cologne8", vcap=128)
     N, steps = 4096, 40
     pairs, va, sig = sc.meta["phase_pairs"], sc.meta["valid_acts"], m.info["signal_ids"]
-    picks = [0, 1, 777, 2048, 4095]
 
     def run():
         g = VecSim(m, N, seed=11)
+        g.select_outputs("drq_norm")
         g.reset(11, 0)
         g.observe()
         acts = []
         for _ in range(steps):
             a = g.policy_maxpressure(pairs, va, sig)
-            acts.append(a[picks].cpu().numpy().copy())
+            acts.append(a.cpu().numpy().copy())
             g.env_step(a)
         return g, acts
 
     g, acts = run()
+    shape = g.launch_shape()
+    assert (shape["threads_per_instance"], shape["instances_per_cta"]) == (64, 8), shape
     st = g.stats()
-    assert (st["anomalies"] == 0).all()
+    assert (st["anomalies"] == 0).all() and (st["n_cap_refused"] == 0).all()
     assert (st["n_inserted"] == st["n_arrived"] + st["n_active"]).all()
     assert (st["tick"] == steps * m.struct.step_length).all()
     assert len(np.unique(st["sum_delay_running"])) > N // 2          # instances really differ (driver randomness)
     og = g.obs()
-    for j, i in enumerate(picks):
-        o = OracleSim(m, 1, seed=11)
-        o.reset(11, i)
-        o.observe()
-        for s in range(steps):
-            o.env_step(acts[s][j:j + 1])
-        vo, vg = o.vehicles(0), g.vehicles(i)
-        for k in util.VEH_EXACT:
-            assert np.array_equal(vo[k], vg[k]), (i, k)
-        oo = o.obs()
-        for k in util.OBS_EXACT:
-            assert np.array_equal(oo[k][0], og[k][i]), (i, k)
+    o = OracleSim(m, N, seed=11)
+    o.reset(11, 0)
+    o.observe()
+    for s in range(steps):
+        # the device policy's actions are themselves checked: the oracle's observations must select the same ones
+        assert np.array_equal(util.maxpressure_actions(sc, m, o.obs()["mplight"]), acts[s]), f"actions differ at step {s}"
+        o.env_step(acts[s])
+    util.assert_same_obs(og, o.obs(), "4096 instances")
+    util.assert_same_stats(st, o.stats(), "4096 instances")
+    for i in (0, 1, 7, 8, 777, 2048, 4088, 4095):
+        util.assert_same_state(g, o, i, f"instance {i}")
     g2, _ = run()
-    st2 = g2.stats()
-    for k in st.dtype.names:
-        assert np.array_equal(st[k], st2[k]), k
+    util.assert_same_stats(st, g2.stats(), "second run")
     assert np.array_equal(g2.obs()["mplight"], og["mplight"])
 
 
@@ -258,6 +265,7 @@ def test_edge_cases(case):
         assert np.array_equal(sg[k], so[k]), (case, k)
     if case == "tile_full":
         assert (sg["n_active"] <= 24).all() and (sg["n_backlog"] > 0).any()
+        assert (sg["n_cap_refused"] > 0).all()           # the truncation is reported, not silent
     if case == "deterministic_driver":
         assert (g.vehicles(0)["sf"] == 1.0).all()
 
@@ -300,3 +308,14 @@ def test_batched_fma2c_matches_dict_view(map_name, key):
                 np.testing.assert_allclose(float(rew_b[k][inst]), float(ref_r[k]), rtol=1e-5, atol=1e-4,
                                            err_msg=f"step {step} reward {k}")
     env.close()
+
+
+@pytest.mark.parametrize("map_name,key,rkey", [("cologne3", "drq_norm", "wait_norm"), ("ingolstadt21", "drq_norm", "pressure"),
+                                               ("ingolstadt21", "drq", "wait"), ("cologne8", "mplight_full", "pressure"),
+                                               ("cologne8", "mplight", "pressure"), ("cologne1", "wave", "wait")])
+def test_batched_states_from_the_kernel_match_dict_view(map_name, key, rkey):
+    """states.{drq, drq_norm, mplight_full, mplight, wave}.batched + rewards.*.batched are tensors the CUDA observe step
+    writes (RS_OUT_* outputs; C3 = ingolstadt21 / drq_norm + wait_norm + pressure); against the per-instance dict
+    callables the reference's goldens pin, on instances 0 and 2 of a 3-instance CUDA batch."""
+    from test_multi_signal_host import batched_vs_dict
+    batched_vs_dict(map_name, key, rkey, None)

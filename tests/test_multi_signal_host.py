@@ -73,17 +73,21 @@ def test_unsupported_arguments_are_refused_loudly():
                                                ("cologne1", "wave", "wait"), ("ingolstadt21", "drq", "pressure"),
                                                ("cologne8", "mplight_full", "pressure")])
 def test_batched_callables_match_the_dict_view_on_the_oracle(map_name, key, rkey):
-    """`.batched(env)` tensor expressions (static gather plans; arrivals / departures from lane_arrivals and
-    presence_counts) against the per-instance dict callables the reference goldens pin, N = 3 oracle instances."""
-    import util
+    """`.batched(env)` device tensors (kernel outputs; static gather plans for FMA2C; arrivals / departures from
+    lane_arrivals and presence_counts) against the per-instance dict callables the reference goldens pin, N = 3."""
     from pyoracle import OracleSim
+    batched_vs_dict(map_name, key, rkey, lambda m: OracleSim(m, 3, seed=0))
+
+
+def batched_vs_dict(map_name, key, rkey, backend):
+    import util
     sc = util.load(map_name)
     mc = sc.meta["map_config"]
     sfn = getattr(states, key)
     rfn = getattr(rewards, rkey)
     n_env = 3
     env = MultiSignal("host", map_name, None, sfn, rfn, step_length=mc["step_length"], yellow_length=mc["yellow_length"],
-                      log_dir=None, n_env=n_env, seed=5, backend=lambda m: OracleSim(m, n_env, seed=0))
+                      log_dir=None, n_env=n_env, seed=5, backend=backend)
     ng = np.array([len(env.phases[ts]) for ts in env.signal_ids])
     for inst in (0, 2):
         env.run = 0
@@ -106,14 +110,14 @@ def _cmp_obs(env, key, got, ref, inst, ctx):
     if isinstance(got, dict):
         assert list(got.keys()) == list(ref.keys())
         for k in ref:
-            np.testing.assert_allclose(got[k][inst].numpy(), ref[k], rtol=1e-5, atol=1e-6, err_msg=f"{ctx} obs {k}")
+            np.testing.assert_allclose(got[k][inst].cpu().numpy(), ref[k], rtol=1e-5, atol=1e-6, err_msg=f"{ctx} obs {k}")
     elif key.startswith("drq"):      # [N, n_sig_lanes, 5] rows, signal-major; the dict view is [1, lanes, 5] per signal
         for s, ts in enumerate(env.signal_ids):
-            np.testing.assert_allclose(got[inst, env.sig_lane_slices[s]].numpy(), np.asarray(ref[ts])[0], rtol=1e-5,
+            np.testing.assert_allclose(got[inst, env.sig_lane_slices[s]].cpu().numpy(), np.asarray(ref[ts])[0], rtol=1e-5,
                                        atol=1e-6, err_msg=f"{ctx} obs {ts}")
     else:                            # mplight / wave: [N, S, 13 | 12]
         for s, ts in enumerate(env.signal_ids):
-            np.testing.assert_allclose(got[inst, s].numpy(), np.asarray(ref[ts]), rtol=1e-5, atol=1e-5, err_msg=f"{ctx} obs {ts}")
+            np.testing.assert_allclose(got[inst, s].cpu().numpy(), np.asarray(ref[ts]), rtol=1e-5, atol=1e-5, err_msg=f"{ctx} obs {ts}")
 
 
 def test_epymarl_registration_mirrors_the_reference(tmp_path):

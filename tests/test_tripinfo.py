@@ -35,6 +35,14 @@ def _check(env, path, st):
     want = (float(st["sum_delay_arrived"]) + float(st["sum_delay_running"])) / (st["n_arrived"] + st["n_active"])
     got = avg_delay_from_tripinfo(path)
     assert abs(got - want) < 0.02, (got, want)          # XML carries 2 decimals
+    # waitingTime (utils/readXML.py metric 'waitingTime' -> utils/avg_waitingTime.py): seconds with speed < 0.1 m/s;
+    # whole seconds, never longer than the trip, and the finished trips add up to RsStats.sum_wait_arrived
+    waits = np.array([float(e.get("waitingTime")) for e in entries])
+    durs = np.array([float(e.get("duration")) for e in entries])
+    assert (waits == np.round(waits)).all() and (waits <= durs + 1e-6).all() and waits.max() > 0
+    done = np.array([float(e.get("arrival")) >= 0 for e in entries])
+    assert abs(waits[done].sum() - float(st["sum_wait_arrived"])) < 1e-3
+    assert abs(avg_delay_from_tripinfo(path, metric="waitingTime") - waits.mean()) < 1e-9
 
 
 def test_tripinfo_cpu(tmp_path):
@@ -73,3 +81,37 @@ def test_never_departed_rule(tmp_path):
     got = avg_delay_from_tripinfo(str(p), sc, end_time=3600.0, vehicle_demand=True)
     assert abs(got - want) < 1e-9
     assert abs(avg_delay_from_tripinfo(str(p)) - (13.0 / 2)) < 1e-12
+
+
+def test_waiting_time_is_the_count_of_halted_seconds():
+    """the per-vehicle accumulator behind tripinfo waitingTime: +1 for every tick the vehicle ends below 0.1 m/s"""
+    from pyoracle import OracleSim
+    sc, m = util.marshal_map("cologne1", controlled=False)
+    o = OracleSim(m, 1, seed=4)
+    o.reset(4, 0)
+    halted, before = {}, set()
+    for _ in range(600):
+        o.tick(1)
+        v = o.vehicles(0)
+        for vid, sp in zip(v["vid"], v["speed"]):
+            if sp < 0.1 and int(vid) in before:      # a vehicle makes its first move in the tick AFTER its insertion
+                halted[int(vid)] = halted.get(int(vid), 0) + 1
+        before = set(int(x) for x in v["vid"])
+    v = o.vehicles(0)
+    assert len(v["vid"]) > 5
+    for vid, aw in zip(v["vid"], v["acc_wait"]):
+        assert aw == halted.get(int(vid), 0)
+
+
+def test_capacity_refusals_are_counted():
+    """RsStats.n_cap_refused: zero with room to spare, positive and equal to the per-tick refusals when the vehicle
+    store is far too small; the refused trips stay in the backlog (insertion is put off, never dropped)."""
+    from pyoracle import OracleSim
+    sc, m = util.marshal_map("cologne8", controlled=False)
+    o = OracleSim(m, 1, seed=1); o.reset(1, 0); o.tick(900)
+    assert o.stats()["n_cap_refused"][0] == 0
+    sc, m = util.marshal_map("cologne8", controlled=False, vcap=16)
+    o = OracleSim(m, 1, seed=1); o.reset(1, 0); o.tick(900)
+    st = o.stats()
+    assert st["n_cap_refused"][0] > 0 and st["n_active"][0] <= 16 and st["n_backlog"][0] > 0
+    assert st["n_inserted"][0] == st["n_arrived"][0] + st["n_active"][0]
