@@ -131,6 +131,10 @@ typedef struct RsScenario {
   int32_t vcap;                      /* max concurrently active vehicles per instance */
   int32_t lane_change;               /* 0 disables the lane-change decision */
   int32_t record_trips;              /* keep a per-trip arrival record (tripinfo output); trip-table demand only */
+  int32_t tile_vcap;                 /* vehicles of an instance the env-step kernel keeps in shared memory (0: chosen from
+                                      * the map's size).  Performance only: an instance that outgrows the tile is stepped
+                                      * by the overflow pass out of a global-memory workspace with room for all `vcap`
+                                      * vehicles; results do not depend on this value. */
 } RsScenario;
 
 /* Optional observation tensors, off by default (rs_select_outputs): each costs its stores every env step. */
@@ -235,6 +239,45 @@ int rs_policy_maxpressure(RsSim* sim, const int32_t* h_pairs, int32_t n_pairs, c
  * 0 for states.wave; agents/maxpressure.py:15-17).  No device work, no RsSim. */
 int rs_host_agent_wave(const float* h_obs, int32_t n_env, int32_t n_signals, int32_t obs_dim, int32_t skip,
                        const int32_t* pairs, int32_t n_pairs, const int32_t* order, int32_t* h_actions);
+/* ---- agent front ends of shared-policy / exploring agents ----
+ * FRAP, the Q-network of MPLight (agents/mplight.py:43-131): parameters as host float arrays in the reference module's
+ * own names and PyTorch layouts (a state_dict's tensors, C-contiguous); demand_shape = 1 (agent_config.py MPLight). */
+typedef struct RsFrapParams {
+  const float* p_weight;                  /* [2, 4]   */
+  const float* d_weight;                  /* [4, 1]   */
+  const float* d_bias;                    /* [4]      */
+  const float* lane_embedding_weight;     /* [16, 8]  */
+  const float* lane_embedding_bias;       /* [16]     */
+  const float* lane_conv_weight;          /* [20, 32, 1, 1] */
+  const float* lane_conv_bias;            /* [20]     */
+  const float* relation_embedding_weight; /* [2, 4]   */
+  const float* relation_conv_weight;      /* [20, 4, 1, 1] */
+  const float* relation_conv_bias;        /* [20]     */
+  const float* hidden_layer_weight;       /* [20, 20, 1, 1] */
+  const float* hidden_layer_bias;         /* [20]     */
+  const float* before_merge_weight;       /* [1, 20, 1, 1] */
+  const float* before_merge_bias;         /* [1]      */
+} RsFrapParams;
+/* Upload the network and the action tables: pairs [n_pairs, 2] (signal_configs[map]['phase_pairs'], n_pairs <= 16),
+ * order [S, n_pairs, 2] as for rs_policy_maxpressure (valid_acts in the reference's scan order). */
+int rs_frap_load(RsSim* sim, const RsFrapParams* params, const int32_t* h_pairs, int32_t n_pairs, const int32_t* h_order);
+/* Q-values + greedy valid action for every (instance, signal) row.  d_obs: [n_env_rows, S, 13] states.mplight rows on
+ * the device, or NULL for the sim's own observation (then n_env_rows is ignored) -- a rank that evaluates the shared
+ * policy for all ranks passes the all-gathered tensor.  d_actions_out [n_env_rows, S] (NULL: the sim's own action
+ * buffer, consumed by rs_env_step_policy); d_q_out [n_env_rows, S, n_pairs] or NULL. */
+int rs_policy_frap(RsSim* sim, const float* d_obs, int32_t n_env_rows, int32_t* d_actions_out, float* d_q_out, void* stream);
+/* Uniform random green phase per signal (epsilon = 1 exploration, agents/pfrl_dqn.py:57-70): Philox keyed by (seed, global
+ * instance id, signal, instance tick), so the draw does not depend on the batch or the GPU the instance runs on. */
+int rs_policy_random(RsSim* sim, uint64_t seed, int32_t* d_actions_out, void* stream);
+/* One whole agent step as a single CUDA-graph launch: the policy kernel over the sim's current observation
+ * (RS_POLICY_*; tables from rs_policy_maxpressure / rs_frap_load must have been uploaded by one ordinary call
+ * before) followed by the fused env step on its actions.  The graph is captured on first use and re-captured when the
+ * episode seed or the output selection changes. */
+#define RS_POLICY_MAXPRESSURE 1
+#define RS_POLICY_MAXWAVE 2
+#define RS_POLICY_FRAP 3
+#define RS_POLICY_RANDOM 4
+int rs_env_step_policy(RsSim* sim, int32_t policy, uint64_t policy_seed, void* stream);
 int rs_get_obs(RsSim* sim, RsObsView* out);
 int rs_get_stats(RsSim* sim, RsStats* h_out /* [N] */);
 /* Dump one instance's vehicles to host arrays (TraCI getters of the N=1 facade; parity tests).
@@ -255,9 +298,14 @@ int rs_set_host_obs(RsSim* sim, int32_t kind, int32_t* floats_per_instance);
 int64_t rs_kernel_launches(RsSim* sim);
 /* launch shape chosen for this scenario (diagnostics / bench `config`): threads per instance, instances per CTA,
  * CTAs in the persistent grid, dynamic shared memory per CTA, tile buffers in shared memory (2 = ping-pong,
- * 1 = re-sort through registers).  Any pointer may be NULL. */
+ * 1 = re-sort through registers, 0 = the vehicle store does not fit shared memory and lives in a per-CTA global-memory
+ * workspace).  Any pointer may be NULL. */
 int rs_get_launch_shape(RsSim* sim, int32_t* threads_per_instance, int32_t* instances_per_cta, int32_t* grid_ctas,
                         int32_t* smem_bytes_per_cta, int32_t* tile_buffers);
+/* the vehicle store and the tile (diagnostics / bench `config`): vehicles per instance in the fast pass's tile and in
+ * the HBM store, whether an overflow pass exists (tile < store), and how many instances the LAST launch deferred to
+ * it (synchronises the device).  Any pointer may be NULL. */
+int rs_get_tile_info(RsSim* sim, int32_t* tile_vcap, int32_t* store_vcap, int32_t* has_overflow_pass, int32_t* last_deferred);
 /* device time (ms) of the last rs_env_step's kernels, CUDA events on the launching stream */
 int rs_last_step_ms(RsSim* sim, float* ms);
 

@@ -49,7 +49,7 @@ _PTRS: List[Tuple[str, object]] = [
 _PARAMS = [("synthetic", C.c_int32), ("synthetic_vtype", C.c_int32), ("step_length", C.c_int32),
            ("yellow_length", C.c_int32), ("end_tick", C.c_int32), ("max_distance", C.c_float),
            ("sigma_override", C.c_float), ("speed_dev_override", C.c_float), ("vcap", C.c_int32),
-           ("lane_change", C.c_int32), ("record_trips", C.c_int32)]
+           ("lane_change", C.c_int32), ("record_trips", C.c_int32), ("tile_vcap", C.c_int32)]
 
 
 class RsScenario(C.Structure):
@@ -124,7 +124,7 @@ def _ptr(arr: np.ndarray, ctype):
 def marshal(sc: Scenario, *, step_length: int = 10, yellow_length: int = 3, max_distance: float = 200.0,
             end_time: Optional[float] = None, controlled: bool = True, sigma: float = -1.0,
             speed_dev: float = -1.0, vcap: int = 0, lane_change: bool = True, record_trips: bool = False,
-            synthetic: Optional[Dict[str, np.ndarray]] = None) -> Marshalled:
+            synthetic: Optional[Dict[str, np.ndarray]] = None, tile_vcap: int = 0) -> Marshalled:
     """Build the C struct.  ``controlled=False`` keeps every tlLogic on its original program
     (the reference's FIXED rows: SUMO default programs, no Signal objects)."""
     a = sc.arrays
@@ -279,17 +279,16 @@ def marshal(sc: Scenario, *, step_length: int = 10, yellow_length: int = 3, max_
     st.vcap = int(vcap)
     st.lane_change = 1 if lane_change else 0
     st.record_trips = 1 if (record_trips and synthetic is None) else 0
+    st.tile_vcap = int(tile_vcap)
     info = dict(programs_installed=programs_installed, yellow_dicts=yellow_dicts, signal_ids=sig_ids,
                 tls_ids=tls_ids, green_states=green_states_of, vcap=int(vcap), sizes=sizes)
     return Marshalled(st, keep, info)
 
 
-SMEM_BUDGET = 200 * 1024   # bytes of the 227 KB per-CTA shared memory the instance tile may use
-
-
 def smem_bytes(vcap: int, n_lanes: int, n_tls: int, n_signals: int, n_origins: int, n_sig_lanes: int,
                n_vtypes: int) -> int:
-    """Mirror of rs::make_layout (resco_b200/csrc/sim.cu): shared memory of one instance tile."""
+    """Mirror of rs::make_layout (resco_b200/csrc/sim.cu): shared memory of one instance with a ping-pong tile of
+    `vcap` vehicles in shared memory."""
     def al(x):
         return (x + 15) & ~15
     o = 0
@@ -298,6 +297,7 @@ def smem_bytes(vcap: int, n_lanes: int, n_tls: int, n_signals: int, n_origins: i
     o = al(o + vcap * 4)
     for _ in range(4):
         o = al(o + vcap * 2)
+    o = al(o + (2 * vcap + max(n_origins, 1)) * 2)
     o = al(o + (n_lanes + 1) * 2)
     o = al(o + (n_lanes + 1) * 2)
     o = al(o + n_lanes * 4)
@@ -315,21 +315,18 @@ def smem_bytes(vcap: int, n_lanes: int, n_tls: int, n_signals: int, n_origins: i
     if n_sig_lanes * 20 > vcap * 6:      # else the observe scratch shares the plan scratch
         o = al(o + max(n_sig_lanes, 1) * 20)
     o = al(o + 16)
-    o = al(o + (2 * vcap + max(n_origins, 1)) * 2)
     o = al(o + max(n_origins, 1) * 2)
+    o = al(o + ((n_lanes + 31) // 32 + 2) * 4)
     return o
 
 
 def default_vcap(sc: Scenario) -> int:
-    """Concurrent-vehicle capacity per instance: a quarter of the jam capacity of the normal lanes,
-    rounded up to a multiple of 64, clamped to [256, 4096] and to what fits the shared-memory tile."""
+    """Capacity of an instance's vehicle store in HBM: a quarter of the jam capacity of the normal lanes, rounded up to
+    a multiple of 64, clamped to [256, 4096] (44 B per vehicle and instance).  The shared-memory tile the kernel works
+    on is smaller (RsScenario.tile_vcap); instances that outgrow it are stepped out of a global-memory workspace, so
+    this number bounds memory, not speed."""
     a = sc.arrays
     normal = a["lane_internal"] == 0
     jam = float(np.sum(np.floor(a["lane_len"][normal] / 7.5) + 1))
     v = int(np.ceil(jam / 4 / 64.0)) * 64
-    v = int(min(max(v, 256), 4096))
-    n_sig_lanes = int(a["sig_lane_off"][-1]) if "sig_lane_off" in a else 0
-    while v > 64 and smem_bytes(v, sc.n_lanes, sc.n_tls, len(sc.meta["signal_ids"]), len(a["origin_lane"]),
-                                n_sig_lanes, len(a["vtype_bit"])) > SMEM_BUDGET:
-        v -= 64
-    return v
+    return int(min(max(v, 256), 4096))

@@ -1,0 +1,175 @@
+// agents.cuh -- batched agent front ends on the device: the act() side of the loop for
+// thousands of lock-step instances, so that a shared-policy step is kernel launches, not a Python loop.
+//
+//   k_policy_frap    forward of the reference's FRAP Q-network (agents/mplight.py:43-131, the model of MPLight) over
+//                    states.mplight rows + greedy choice among the signal's valid actions (agents/agent.py:46-60)
+//   k_policy_random  uniform random green phase per signal (the epsilon = 1 exploration of IDQN / IPPO / MPLight,
+//                    agents/pfrl_dqn.py:57-70), Philox keyed by (seed, global instance id, signal, tick)
+//
+// (MAXPRESSURE / MAXWAVE: k_policy in sim.cu.)  Plain fp32 on the CUDA cores: one row is 13 x 12 pair competitions
+// of a 20 x 20 layer -- there is no batched-GEMM shape worth a tensor-core tile here and the argmax has to agree with
+// the reference's fp32 Q-values.
+#pragma once
+#include "sim_kernels.cuh"
+
+namespace rs {
+
+// parameter block of FRAP in one float array (offsets in floats); names and shapes of agents/mplight.py:59-71
+enum FrapOff {
+  FP_P = 0,            // p.weight                  [2][4]
+  FP_DW = 8,           // d.weight                  [4][1]   (demand_shape = 1)
+  FP_DB = 12,          // d.bias                    [4]
+  FP_LEW = 16,         // lane_embedding.weight     [16][8]
+  FP_LEB = 144,        // lane_embedding.bias       [16]
+  FP_LCW = 160,        // lane_conv.weight          [20][32]
+  FP_LCB = 800,        // lane_conv.bias            [20]
+  FP_REW = 820,        // relation_embedding.weight [2][4]
+  FP_RCW = 828,        // relation_conv.weight      [20][4]
+  FP_RCB = 908,        // relation_conv.bias        [20]
+  FP_HLW = 928,        // hidden_layer.weight       [20][20]
+  FP_HLB = 1328,       // hidden_layer.bias         [20]
+  FP_BMW = 1348,       // before_merge.weight       [1][20]
+  FP_BMB = 1368,       // before_merge.bias         [1]
+  FP_TOTAL = 1369
+};
+constexpr int kFrapMaxPairs = 16;
+constexpr int kFrapThreads = 128;
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// derived, batch-independent tables (computed once per block into shared memory)
+struct FrapShared {
+  float w[FP_TOTAL];
+  float ph_part[2][16];   // lane_embedding over the phase half of its input (+ bias), for "movement in the phase" 0 / 1
+  float rel[2][20];       // relation branch for competition-mask values 0 / 1 (mplight.py:116-119)
+};
+
+// obs: [rows][13] states.mplight (phase index, 12 pressures); pairs [n_pairs][2]; comp [n_pairs][n_pairs - 1] 0/1;
+// order [S][n_pairs][2] = (pair index, action) in the reference's evaluation order, -1 terminates (k_policy's table);
+// q_out [rows][n_pairs] or null; actions [rows].
+__global__ void __launch_bounds__(kFrapThreads) k_policy_frap(const float* __restrict__ obs, int rows, int n_signals,
+                                                              const float* __restrict__ params, const int32_t* __restrict__ pairs,
+                                                              int n_pairs, const uint8_t* __restrict__ comp,
+                                                              const int32_t* __restrict__ order, float* __restrict__ q_out,
+                                                              int32_t* __restrict__ actions) {
+  extern __shared__ __align__(16) unsigned char fsm[];
+  FrapShared& F = *reinterpret_cast<FrapShared*>(fsm);
+  const int R = kFrapThreads / n_pairs;                 // rows per block
+  float* pd = reinterpret_cast<float*>(fsm + sizeof(FrapShared));        // [R][12][16]
+  float* fs = pd + R * 12 * 16;                                          // [R][n_pairs][40]: first (20) | second (20)
+  float* qs = fs + R * n_pairs * 40;                                     // [R][n_pairs]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < FP_TOTAL; i += kFrapThreads) F.w[i] = __ldg(params + i);
+  __syncthreads();
+  if (tid < 32) {
+    const int e = tid >> 4, u = tid & 15;
+    float acc = F.w[FP_LEB + u];
+    for (int c = 0; c < 4; ++c) acc = __fmaf_rn(F.w[FP_LEW + u * 8 + c], sigmoidf_(F.w[FP_P + e * 4 + c]), acc);
+    F.ph_part[e][u] = acc;
+  } else if (tid < 72) {
+    const int e = (tid - 32) / 20, k = (tid - 32) % 20;
+    float acc = F.w[FP_RCB + k];
+    for (int c = 0; c < 4; ++c) acc = __fmaf_rn(F.w[FP_RCW + k * 4 + c], fmaxf(F.w[FP_REW + e * 4 + c], 0.0f), acc);
+    F.rel[e][k] = fmaxf(acc, 0.0f);
+  }
+  __syncthreads();
+  const int row0 = blockIdx.x * R;
+  // ---- A: per movement: relu(lane_embedding(cat(sigmoid(p[in phase]), sigmoid(d(x))))) ----
+  for (int x = tid; x < R * 12 * 16; x += kFrapThreads) {
+    const int r = x / 192, m = (x / 16) % 12, u = x & 15;
+    const int row = row0 + r;
+    float v = 0.0f;
+    if (row < rows) {
+      const float* ob = obs + (size_t)row * 13;
+      const int act = (int)__ldg(ob);
+      int e = 0;
+      if (act >= 0 && act < n_pairs) e = (m == __ldg(pairs + 2 * act) || m == __ldg(pairs + 2 * act + 1)) ? 1 : 0;
+      const float xm = __ldg(ob + 1 + m);
+      float acc = F.ph_part[e][u];
+      for (int c = 0; c < 4; ++c)
+        acc = __fmaf_rn(F.w[FP_LEW + u * 8 + 4 + c], sigmoidf_(__fmaf_rn(F.w[FP_DW + c], xm, F.w[FP_DB + c])), acc);
+      v = fmaxf(acc, 0.0f);
+    }
+    pd[x] = v;
+  }
+  __syncthreads();
+  // ---- B: pair embeddings through the two halves of the 1x1 lane convolution ----
+  for (int x = tid; x < R * n_pairs * 40; x += kFrapThreads) {
+    const int r = x / (n_pairs * 40), i = (x / 40) % n_pairs, k = x % 40;
+    const float* pa = pd + (r * 12 + __ldg(pairs + 2 * i)) * 16;
+    const float* pb = pd + (r * 12 + __ldg(pairs + 2 * i + 1)) * 16;
+    const int kk = k < 20 ? k : k - 20;
+    const float* wrow = F.w + FP_LCW + kk * 32 + (k < 20 ? 0 : 16);
+    float acc = k < 20 ? F.w[FP_LCB + kk] : 0.0f;
+    for (int u = 0; u < 16; ++u) acc = __fmaf_rn(wrow[u], pa[u] + pb[u], acc);
+    fs[x] = acc;
+  }
+  __syncthreads();
+  // ---- C: pair competition: one thread per (row, pair i), the n - 1 opponents two at a time ----
+  const int r = tid / n_pairs, i = tid % n_pairs;
+  if (r < R) {
+    const float* first = fs + (r * n_pairs + i) * 40;
+    float f[20];
+#pragma unroll
+    for (int k = 0; k < 20; ++k) f[k] = first[k];
+    float q = 0.0f;
+    for (int jj = 0; jj < n_pairs - 1; jj += 2) {
+      const bool two = jj + 1 < n_pairs - 1;
+      const int j0 = jj < i ? jj : jj + 1, j1 = two ? (jj + 1 < i ? jj + 1 : jj + 2) : j0;
+      const float* s0 = fs + (r * n_pairs + j0) * 40 + 20;
+      const float* s1 = fs + (r * n_pairs + j1) * 40 + 20;
+      const float* r0 = F.rel[__ldg(comp + i * (n_pairs - 1) + jj)];
+      const float* r1 = F.rel[__ldg(comp + i * (n_pairs - 1) + (two ? jj + 1 : jj))];
+      float c0[20], c1[20];
+#pragma unroll
+      for (int k = 0; k < 20; ++k) { c0[k] = fmaxf(f[k] + s0[k], 0.0f) * r0[k]; c1[k] = fmaxf(f[k] + s1[k], 0.0f) * r1[k]; }
+      float o0 = F.w[FP_BMB], o1 = F.w[FP_BMB];
+#pragma unroll 4
+      for (int k2 = 0; k2 < 20; ++k2) {
+        const float* w = F.w + FP_HLW + k2 * 20;
+        float h0 = F.w[FP_HLB + k2], h1 = h0;
+#pragma unroll
+        for (int k = 0; k < 20; ++k) { const float wk = w[k]; h0 = __fmaf_rn(wk, c0[k], h0); h1 = __fmaf_rn(wk, c1[k], h1); }
+        const float bm = F.w[FP_BMW + k2];
+        o0 = __fmaf_rn(bm, fmaxf(h0, 0.0f), o0); o1 = __fmaf_rn(bm, fmaxf(h1, 0.0f), o1);
+      }
+      q += o0;
+      if (two) q += o1;
+    }
+    qs[r * n_pairs + i] = q;
+    const int row = row0 + r;
+    if (row < rows && q_out) q_out[(size_t)row * n_pairs + i] = q;
+  }
+  __syncthreads();
+  // ---- greedy action among the signal's valid pairs, first maximum in the reference's scan order ----
+  if (tid < R && row0 + tid < rows) {
+    const int row = row0 + tid, sg = row % n_signals;
+    float best = 0.0f; int bi = -1;
+    for (int k = 0; k < n_pairs; ++k) {
+      const int p = __ldg(order + (sg * n_pairs + k) * 2);
+      if (p < 0) break;
+      const float v = qs[tid * n_pairs + p];
+      if (bi < 0 || v > best) { best = v; bi = __ldg(order + (sg * n_pairs + k) * 2 + 1); }
+    }
+    actions[row] = bi < 0 ? 0 : bi;
+  }
+}
+
+inline size_t frap_smem_bytes(int n_pairs) {
+  const int R = kFrapThreads / n_pairs;
+  return sizeof(FrapShared) + sizeof(float) * ((size_t)R * 12 * 16 + (size_t)R * n_pairs * 40 + (size_t)R * n_pairs);
+}
+
+// uniform random green phase: Philox keyed by (seed, global instance id, signal, instance tick)
+__global__ void k_policy_random(DevSim D, uint64_t seed, int32_t* actions) {
+  const DevScenario& sc = D.sc;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= D.n_env * sc.n_signals) return;
+  const int env = x / sc.n_signals, sg = x % sc.n_signals;
+  const uint64_t id = (uint64_t)(D.first_env_id + env);
+  uint32_t c[4] = {(uint32_t)id, (uint32_t)(id >> 32), (uint32_t)sg, (uint32_t)D.hdr[(size_t)env * kHdrInts + H_TICK]};
+  philox(c, (uint32_t)seed ^ 0x5EED5EEDu, (uint32_t)(seed >> 32));
+  actions[x] = (int32_t)(c[0] % (uint32_t)__ldg(sc.sig_n_green + sg));
+}
+
+}  // namespace rs

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "sim_kernels.cuh"
+#include "agents.cuh"
 
 namespace rs {
 
@@ -18,19 +19,23 @@ namespace rs {
 struct SmemLayout {
   int vcap, L, n_tls, S, O, SL, n_vt;
   int single;   // one tile buffer: the per-tick re-sort goes through registers (vcap <= 2 x threads per instance)
-  size_t off_bufA, off_bufB, off_vn, off_newlane, off_newidx, off_mnext, off_arr;
+  int gmem;     // the per-vehicle region lives in global memory (DevSim::workspace); offsets below it restart at 0
+  // per-vehicle region (offsets from the vehicle-region base: shared memory, or the CTA's workspace slot)
+  size_t off_bufA, off_bufB, off_vn, off_newlane, off_newidx, off_mnext, off_arr, off_dirty;
+  size_t veh_total;
+  // per-lane / per-signal / per-origin region (offsets from the instance's shared-memory base)
   size_t off_lane_start, off_start2, off_cnt2, off_mhead;
   size_t off_tls_phase, off_tls_end, off_tls_state, off_next_phase, off_origin_cur, off_origin_backlog, off_origin_cand;
-  size_t off_vt, off_hdr, off_misc, off_obs, off_mbar, off_dirty, off_oklist, off_occ;
-  size_t total;
+  size_t off_vt, off_hdr, off_misc, off_obs, off_mbar, off_oklist, off_occ;
+  size_t total;   // shared memory per instance
 };
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 __host__ __device__ inline SmemLayout make_layout(const DevScenario& sc) {
   SmemLayout m;
-  m.single = sc.tile_single;
-  m.vcap = sc.vcap; m.L = sc.n_lanes; m.n_tls = sc.n_tls; m.S = sc.n_signals; m.O = sc.n_origins;
+  m.single = sc.tile_single; m.gmem = sc.tile_gmem;
+  m.vcap = sc.tile_cap; m.L = sc.n_lanes; m.n_tls = sc.n_tls; m.S = sc.n_signals; m.O = sc.n_origins;
   m.SL = sc.n_sig_lanes; m.n_vt = sc.n_vtypes;
   size_t o = 0;
   m.off_bufA = o; o = align16(o + (size_t)kVehWords * m.vcap * 4);
@@ -40,6 +45,9 @@ __host__ __device__ inline SmemLayout make_layout(const DevScenario& sc) {
   m.off_newidx = o; o = align16(o + (size_t)m.vcap * 2);
   m.off_mnext = o; o = align16(o + (size_t)m.vcap * 2);
   m.off_arr = o; o = align16(o + (size_t)m.vcap * 2);
+  m.off_dirty = o; o = align16(o + ((size_t)2 * m.vcap + (size_t)(m.O > 0 ? m.O : 1)) * 2);   // lanes touched this tick
+  m.veh_total = o;
+  if (m.gmem) o = 0;
   m.off_lane_start = o; o = align16(o + (size_t)(m.L + 1) * 2);
   m.off_start2 = o; o = align16(o + (size_t)(m.L + 1) * 2);
   m.off_cnt2 = o; o = align16(o + (size_t)m.L * 4);
@@ -55,11 +63,10 @@ __host__ __device__ inline SmemLayout make_layout(const DevScenario& sc) {
   m.off_hdr = o; o = align16(o + (size_t)kHdrInts * 4);
   m.off_misc = o; o = align16(o + 48 * 4);
   // the per-lane observation scratch is only live in observe_body: it shares the plan scratch (vn + newlane, which
-  // are contiguous) when it fits there
-  if ((size_t)m.SL * 5 * 4 <= (size_t)m.vcap * 6) m.off_obs = m.off_vn;
+  // are contiguous) when that is in shared memory and it fits there; ~0 = "lives at off_vn of the vehicle region"
+  if (!m.gmem && (size_t)m.SL * 5 * 4 <= (size_t)m.vcap * 6) m.off_obs = ~(size_t)0;
   else { m.off_obs = o; o = align16(o + (size_t)(m.SL > 0 ? m.SL : 1) * 5 * 4); }
   m.off_mbar = o; o = align16(o + 16);
-  m.off_dirty = o; o = align16(o + ((size_t)2 * m.vcap + (size_t)(m.O > 0 ? m.O : 1)) * 2);   // lanes touched this tick
   m.off_oklist = o; o = align16(o + (size_t)(m.O > 0 ? m.O : 1) * 2);                          // origins with a candidate
   m.off_occ = o; o = align16(o + ((size_t)(m.L + 31) / 32 + 2) * 4);                          // lane-occupancy bits
   m.total = o;
@@ -81,7 +88,7 @@ __shared__ long long s_pclk_last;
 enum { PC_STAGE = 0, PC_S0, PC_S1, PC_S2, PC_S3A, PC_S3B, PC_S4, PC_S5, PC_S6, PC_S7, PC_OBS, PC_WRITE, PC_SCHED, PC_N };
 
 // misc slots
-enum { M_NARR = 0, M_NOK, M_NAFTER, M_NDIRTY, M_NOKC, M_WARP = 16 /* 32 ints of warp totals */ };
+enum { M_NARR = 0, M_NOK, M_NAFTER, M_NDIRTY, M_NOKC, M_BAIL /* the instance outgrew the tile: its step is redone by the overflow pass */, M_WARP = 16 /* 32 ints of warp totals */ };
 
 constexpr int kDirty = 0x40000000;   // flag bit in cnt2[l]: the lane gained or lost a vehicle this tick
 
@@ -106,18 +113,18 @@ struct OriginCand { int32_t vid; uint16_t route; int16_t ok_dd; int32_t vt; };  
 
 // ------------------------------------------------------------------------------------------------
 template <int BLOCK, int G>
-__device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, unsigned char* smem, Tile& T, uint32_t*& cur,
-                          uint32_t*& oth, uint16_t*& start2, const int env) {
+__device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, unsigned char* smem, unsigned char* vb, Tile& T,
+                          uint32_t*& cur, uint32_t*& oth, uint16_t*& start2, const int env) {
   const DevScenario& sc = D.sc;
   const int tid = threadIdx.x % BLOCK;   // BLOCK = threads per instance (a CTA may hold several instances)
   const int L = m.L;
-  float* vn = (float*)(smem + m.off_vn);
-  uint16_t* newlane = (uint16_t*)(smem + m.off_newlane);
-  uint16_t* newidx = (uint16_t*)(smem + m.off_newidx);
-  uint16_t* mnext = (uint16_t*)(smem + m.off_mnext);
-  uint16_t* arr = (uint16_t*)(smem + m.off_arr);
+  float* vn = (float*)(vb + m.off_vn);               // vb: base of the per-vehicle region (shared memory or workspace)
+  uint16_t* newlane = (uint16_t*)(vb + m.off_newlane);
+  uint16_t* newidx = (uint16_t*)(vb + m.off_newidx);
+  uint16_t* mnext = (uint16_t*)(vb + m.off_mnext);
+  uint16_t* arr = (uint16_t*)(vb + m.off_arr);
   int32_t* cnt2 = (int32_t*)(smem + m.off_cnt2);     // per-lane vehicle count, kept current across ticks
-  uint16_t* dirty = (uint16_t*)(smem + m.off_dirty);
+  uint16_t* dirty = (uint16_t*)(vb + m.off_dirty);
   uint16_t* oklist = (uint16_t*)(smem + m.off_oklist);
   int32_t* mhead = (int32_t*)(smem + m.off_mhead);
   int32_t* hdr = (int32_t*)(smem + m.off_hdr);
@@ -234,10 +241,10 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
     T.meta[i] = mt;
     if (curl < 0) {
       newlane[i] = (uint16_t)kArrived;
-      if (D.trip_rec)   // tripinfo record (multi_signal.py:127-129)
+      if (D.trip_rec && !misc[M_BAIL])   // tripinfo record (multi_signal.py:127-129); a deferred instance's step is redone
         D.trip_rec[(size_t)env * sc.n_trips + T.vid[i]] =
             make_int4(T.tick, (int)(T.ed[i] >> 16), __float_as_int(T.tloss[i]), (int)(T.dl[i] & 0xFFFFu));
-      if (D.trip_rec) D.trip_wait[(size_t)env * sc.n_trips + T.vid[i]] = (float)(T.aw[i] & 0xFFFFu);
+      if (D.trip_rec && !misc[M_BAIL]) D.trip_wait[(size_t)env * sc.n_trips + T.vid[i]] = (float)(T.aw[i] & 0xFFFFu);
       atomicAdd(&cnt2[l], -1);
       mark_dirty(l);
       int s = atomicAdd(&misc[M_NARR], 1);
@@ -363,6 +370,7 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
   {
     const int n_after = misc[M_NAFTER], n_ok = misc[M_NOK];
     const bool all = n_after + n_ok <= m.vcap;
+    if (!all && D.overflow_count && !D.from_list && tid == 0) misc[M_BAIL] = 1;   // tile outgrown (not the store): defer, do not refuse
     for (int j = tid; j < nokc; j += BLOCK) {
       const int o = oklist[j];
       if (cand[o].ok_dd < 0) continue;
@@ -383,7 +391,7 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
           const int ci = __ldg(sc.origin_off + o) + origin_cur[o];
           origin_backlog[o] = __float_as_int(ci < __ldg(sc.origin_off + o + 1) ? __ldg(sc.trip_depart + ci) : 3.0e38f);
         }
-      } else { cand[o].ok_dd = -2; atomicAdd(&hdr[H_NREF], 1); }   // refused by capacity: counted (RsStats.n_cap_refused); still "ok before" for later origins
+      } else { cand[o].ok_dd = -2; atomicAdd(&hdr[H_NREF], 1); }   // (a deferred instance's counters are never written back)   // refused by capacity: counted (RsStats.n_cap_refused); still "ok before" for later origins
     }
   }
   __syncthreads();
@@ -517,11 +525,11 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
 // ------------------------------------------------------------------------------------------------
 // Signal.observe (traffic_signal.py:189-235) + states.mplight / wave + rewards.* + calc_metrics
 template <int BLOCK>
-__device__ __forceinline__ void observe_body(const DevSim& D, const SmemLayout& m, unsigned char* smem, Tile& T, int env) {
+__device__ __forceinline__ void observe_body(const DevSim& D, const SmemLayout& m, unsigned char* smem, unsigned char* vb, Tile& T, int env) {
   const DevScenario& sc = D.sc;
   const int tid = threadIdx.x % BLOCK, lane_id = tid & 31, wid = tid >> 5, nw = BLOCK / 32;
   int32_t* hdr = (int32_t*)(smem + m.off_hdr);
-  float* ob = (float*)(smem + m.off_obs);   // [5][SL]
+  float* ob = (float*)(m.off_obs == ~(size_t)0 ? vb + m.off_vn : smem + m.off_obs);   // [5][SL]
   const int SL = m.SL, S = m.S;
   const int e = hdr[H_EPOCH];
   const uint32_t eprev = (uint32_t)(e - 1) & 0xFFFFu;
@@ -635,11 +643,12 @@ __device__ __forceinline__ void dev_set_phase(const DevScenario& sc, Tile& T, in
 
 template <int BLOCK, int G>
 __device__ __forceinline__ void run_instance(const DevSim& D, const RunArgs& A, const SmemLayout& m,
-                                             unsigned char* smem, const int env, uint32_t& tma_parity) {
+                                             unsigned char* smem, unsigned char* vb, const int env, const bool real_slot,
+                                             uint32_t& tma_parity) {
   const DevScenario& sc = D.sc;
   const int tid = threadIdx.x % BLOCK;
-  uint32_t* cur = (uint32_t*)(smem + m.off_bufA);
-  uint32_t* oth = (uint32_t*)(smem + m.off_bufB);
+  uint32_t* cur = (uint32_t*)(vb + m.off_bufA);
+  uint32_t* oth = (uint32_t*)(vb + m.off_bufB);
   int32_t* hdr = (int32_t*)(smem + m.off_hdr);
   int32_t* next_phase = (int32_t*)(smem + m.off_next_phase);
   int32_t* origin_cur = (int32_t*)(smem + m.off_origin_cur);
@@ -681,24 +690,31 @@ __device__ __forceinline__ void run_instance(const DevSim& D, const RunArgs& A, 
   }
   for (int i = tid; i < m.n_vt * 8; i += BLOCK) vt[i] = __ldg(sc.vtype + i);
   __syncthreads();
+  int32_t* misc0 = (int32_t*)(smem + m.off_misc);
+  if (tid == 0) {   // already larger than this launch's tile: defer at once and step an empty tile (barriers stay in lock-step)
+    const int big = (D.overflow_count && !D.from_list && hdr[H_NVEH] > m.vcap) ? 1 : 0;
+    misc0[M_BAIL] = big;
+    if (big) hdr[H_NVEH] = 0;
+  }
+  __syncthreads();
   const int n0 = hdr[H_NVEH];
   {
-    const uint32_t* g = D.veh + (size_t)env * kVehWords * m.vcap;
+    const uint32_t* g = D.veh + (size_t)env * kVehWords * sc.vcap;
     const int n4 = (n0 + 3) >> 2;
-    if (D.use_tma) {        // TMA: ten 1-D bulk copies (one per word array) tracked by the slot's mbarrier
+    if (D.use_tma && !m.gmem) {   // TMA: 1-D bulk copies (one per word array) tracked by the slot's mbarrier
       if (n4 > 0) {
         uint64_t* bar = (uint64_t*)(smem + m.off_mbar);
         if (tid == 0) {
           mbar_expect_tx(bar, (uint32_t)(kVehWords * n4 * 16));
           for (int w = 0; w < kVehWords; ++w)
-            tma_load_1d(cur + (size_t)w * m.vcap, g + (size_t)w * m.vcap, (uint32_t)(n4 * 16), bar);
+            tma_load_1d(cur + (size_t)w * m.vcap, g + (size_t)w * sc.vcap, (uint32_t)(n4 * 16), bar);
         }
         mbar_wait(bar, tma_parity);
         tma_parity ^= 1u;
       }
     } else {
       for (int w = 0; w < kVehWords; ++w) {
-        const uint4* src = (const uint4*)(g + (size_t)w * m.vcap);
+        const uint4* src = (const uint4*)(g + (size_t)w * sc.vcap);
         uint4* dst = (uint4*)(cur + (size_t)w * m.vcap);
         for (int i = tid; i < n4; i += BLOCK) dst[i] = __ldcs(src + i);
       }
@@ -756,41 +772,46 @@ __device__ __forceinline__ void run_instance(const DevSim& D, const RunArgs& A, 
       __syncthreads();
     }
     if (k == n_ticks) break;
-    tick_body<BLOCK, G>(D, m, smem, T, cur, oth, start2, env);
+    tick_body<BLOCK, G>(D, m, smem, vb, T, cur, oth, start2, env);
   }
-  if (A.do_observe) observe_body<BLOCK>(D, m, smem, T, env);
+  if (A.do_observe) observe_body<BLOCK>(D, m, smem, vb, T, env);
   PCLK(PC_OBS);
 
-  // ---- write the tile back ----
+  // ---- write the tile back; a deferred instance leaves its HBM state untouched and queues itself for the overflow
+  //      pass (same barriers either way: the instances of a CTA run in lock-step) ----
+  const bool bail = misc0[M_BAIL] != 0;
+  if (bail && tid == 0 && real_slot) D.overflow_list[atomicAdd(D.overflow_count, 1)] = env;
   {
     const int n1 = hdr[H_NVEH];
-    uint32_t* g = D.veh + (size_t)env * kVehWords * m.vcap;
+    uint32_t* g = D.veh + (size_t)env * kVehWords * sc.vcap;
     const int n4 = (n1 + 3) >> 2;
-    if (D.use_tma) {        // shared -> global bulk stores; the tile may be reused once they have been READ
+    if (D.use_tma && !m.gmem) {   // shared -> global bulk stores; the tile may be reused once they have been READ
       fence_proxy_async_smem();
       __syncthreads();
-      if (tid == 0 && n4 > 0) {
+      if (tid == 0 && n4 > 0 && !bail) {
         for (int w = 0; w < kVehWords; ++w)
-          tma_store_1d(g + (size_t)w * m.vcap, cur + (size_t)w * m.vcap, (uint32_t)(n4 * 16));
+          tma_store_1d(g + (size_t)w * sc.vcap, cur + (size_t)w * m.vcap, (uint32_t)(n4 * 16));
         tma_store_commit_and_wait_read();
       }
-    } else {
+    } else if (!bail) {
       for (int w = 0; w < kVehWords; ++w) {
-        uint4* dst = (uint4*)(g + (size_t)w * m.vcap);
+        uint4* dst = (uint4*)(g + (size_t)w * sc.vcap);
         const uint4* src = (const uint4*)(cur + (size_t)w * m.vcap);
         for (int i = tid; i < n4; i += BLOCK) __stcs(dst + i, src[i]);
       }
     }
   }
-  if (tid < kHdrInts) D.hdr[(size_t)env * kHdrInts + tid] = hdr[tid];
-  for (int i = tid; i < m.n_tls; i += BLOCK) {
-    D.tls_phase[(size_t)env * m.n_tls + i] = T.tls_phase[i];
-    D.tls_end[(size_t)env * m.n_tls + i] = T.tls_end[i];
-  }
-  for (int i = tid; i < m.S; i += BLOCK) D.next_phase[(size_t)env * m.S + i] = next_phase[i];
-  for (int i = tid; i < m.O; i += BLOCK) {
-    D.origin_cur[(size_t)env * m.O + i] = origin_cur[i];
-    if (sc.synthetic) D.origin_backlog[(size_t)env * m.O + i] = origin_backlog[i];
+  if (!bail) {
+    if (tid < kHdrInts) D.hdr[(size_t)env * kHdrInts + tid] = hdr[tid];
+    for (int i = tid; i < m.n_tls; i += BLOCK) {
+      D.tls_phase[(size_t)env * m.n_tls + i] = T.tls_phase[i];
+      D.tls_end[(size_t)env * m.n_tls + i] = T.tls_end[i];
+    }
+    for (int i = tid; i < m.S; i += BLOCK) D.next_phase[(size_t)env * m.S + i] = next_phase[i];
+    for (int i = tid; i < m.O; i += BLOCK) {
+      D.origin_cur[(size_t)env * m.O + i] = origin_cur[i];
+      if (sc.synthetic) D.origin_backlog[(size_t)env * m.O + i] = origin_backlog[i];
+    }
   }
   PCLK(PC_WRITE);
 }
@@ -804,6 +825,8 @@ __global__ void __launch_bounds__(TPI * G, MINB) k_run(const __grid_constant__ D
   extern __shared__ __align__(16) unsigned char smem[];
   const SmemLayout m = make_layout(D.sc);
   unsigned char* my = smem + (size_t)(threadIdx.x / TPI) * m.total;
+  // per-vehicle region: the instance slot's shared memory, or (tile_gmem) this CTA's slot of the global workspace
+  unsigned char* vb = m.gmem ? D.workspace + ((size_t)blockIdx.x * G + threadIdx.x / TPI) * m.veh_total : my;
   __shared__ int s_env;
   uint32_t tma_parity = 0;
 #if RS_PHASE_CLOCKS
@@ -821,9 +844,12 @@ __global__ void __launch_bounds__(TPI * G, MINB) k_run(const __grid_constant__ D
     }
     PCLK(PC_SCHED);
     const int env0 = D.persistent ? s_env : (int)blockIdx.x * G;
-    if (env0 >= D.n_env) break;
+    const int n_work = D.from_list ? *D.overflow_count : D.n_env;
+    if (env0 >= n_work) break;
     // a slot past the end of the batch repeats the last instance (same inputs -> identical stores)
-    run_instance<TPI, G>(D, A, m, my, min(env0 + (int)(threadIdx.x / TPI), D.n_env - 1), tma_parity);
+    const int slot = env0 + (int)(threadIdx.x / TPI);
+    const int item = min(slot, n_work - 1);
+    run_instance<TPI, G>(D, A, m, my, vb, D.from_list ? D.overflow_list[item] : item, slot < n_work, tma_parity);
     if (!D.persistent) break;
     __syncthreads();
   }
@@ -938,6 +964,9 @@ struct RsSim {
   int smem_extra;   // RESCO_B200_SMEM_EXTRA: unused dynamic shared memory per CTA (experiments on the L1 / shared split)
   int n_sm;
   int resident_ctas;
+  // overflow pass (see rs_create): same kernel, whole store in the global workspace, instances from overflow_list
+  bool two_pass; SmemLayout layout2; int block2, group2, minb2, resident_ctas2; unsigned char* workspace2;
+  int32_t* counters;   // [0] work counter of the fast pass, [1] of the overflow pass, [2] number of deferred instances
   std::vector<void*> allocs;
   int64_t launches;
   cudaEvent_t ev0, ev1, ev_done;
@@ -949,6 +978,9 @@ struct RsSim {
   RsStats* d_stats;
   int32_t *d_pairs, *d_valid; int n_pairs_alloc;
   int host_obs_kind; size_t host_obs_floats;   // rs_set_host_obs
+  int use_wave_tables;                          // tables of the last rs_policy_maxpressure call
+  float* d_frap; int32_t* d_frap_pairs; uint8_t* d_frap_comp; int32_t* d_frap_order; int frap_pairs;   // rs_frap_load
+  cudaGraphExec_t graph; int graph_policy; uint64_t graph_seed;   // rs_env_step_policy
 };
 
 static thread_local std::string g_err;
@@ -983,13 +1015,10 @@ static int dev_alloc(RsSim* s, T*& out, size_t count) {
 #define TRY(x) do { int _r = (x); if (_r) return _r; } while (0)
 
 template <int TPI, int G, int MINB>
-static int launch_run(RsSim* s, const RunArgs& a, cudaStream_t st) {
-  int grid = (s->d.n_env + G - 1) / G;
-  if (s->d.persistent) {
-    CK(cudaMemsetAsync(s->d.work_counter, 0, sizeof(int32_t), st));
-    if (s->resident_ctas < grid) grid = s->resident_ctas;
-  }
-  k_run<TPI, G, MINB><<<grid, TPI * G, (size_t)s->layout.total * G + s->smem_extra, st>>>(s->d, a);
+static int launch_run(RsSim* s, const DevSim& d, size_t smem_per_instance, int resident, int n_work, const RunArgs& a, cudaStream_t st) {
+  int grid = (n_work + G - 1) / G;
+  if (d.persistent && resident < grid) grid = resident;
+  k_run<TPI, G, MINB><<<grid, TPI * G, smem_per_instance * G + s->smem_extra, st>>>(d, a);
   s->launches += 1;
   CK(cudaGetLastError());
   return 0;
@@ -1000,25 +1029,57 @@ static int launch_run(RsSim* s, const RunArgs& a, cudaStream_t st) {
 #define RS_VARIANTS(X) X(64, 1, 1) X(64, 2, 1) X(64, 4, 1) X(64, 5, 1) X(64, 6, 1) X(64, 7, 1) X(64, 8, 1) X(32, 8, 1) X(32, 16, 1) \
   X(128, 1, 1) X(128, 2, 1) X(128, 4, 1) X(256, 1, 1) X(256, 2, 1) X(512, 1, 1) X(512, 2, 1) X(512, 1, 2)
 
-static int run(RsSim* s, const RunArgs& a, cudaStream_t st) {
-#define X(B, G, M) if (s->block == B && s->group == G && s->minb == M) return launch_run<B, G, M>(s, a, st);
+static int launch_variant(RsSim* s, int block, int group, int minb, const DevSim& d, size_t smem_per_instance, int resident,
+                          int n_work, const RunArgs& a, cudaStream_t st) {
+#define X(B, G, M) if (block == B && group == G && minb == M) return launch_run<B, G, M>(s, d, smem_per_instance, resident, n_work, a, st);
   RS_VARIANTS(X)
 #undef X
   return fail(RS_ERR_INVALID, "unsupported RESCO_B200_BLOCK / RESCO_B200_GROUP / RESCO_B200_REGCAP combination");
 }
 
+// the overflow pass's view of the sim: same state, the whole store as its tile (global workspace), work from the list
+static DevSim overflow_view(const RsSim* s) {
+  DevSim d2 = s->d;
+  d2.sc.tile_cap = d2.sc.vcap; d2.sc.tile_single = 0; d2.sc.tile_gmem = 1;
+  d2.workspace = s->workspace2;
+  d2.work_counter = s->counters + 1;
+  d2.overflow_count = s->counters + 2; d2.from_list = 1;   // from_list: the count is read, nothing is deferred again
+  d2.persistent = 1;
+  return d2;
+}
+
+static int run(RsSim* s, const RunArgs& a, cudaStream_t st) {
+  if (s->d.persistent) CK(cudaMemsetAsync(s->counters, 0, 4 * sizeof(int32_t), st));
+  TRY(launch_variant(s, s->block, s->group, s->minb, s->d, s->layout.total, s->resident_ctas, s->d.n_env, a, st));
+  if (s->two_pass)
+    TRY(launch_variant(s, s->block2, s->group2, s->minb2, overflow_view(s), s->layout2.total, s->resident_ctas2, s->d.n_env, a, st));
+  return 0;
+}
+
 static int configure(RsSim* s) {
-  const int bytes = (int)s->layout.total * s->group + s->smem_extra;
-#define X(B, G, M) if (s->block == B && s->group == G && s->minb == M) { \
+  // shared memory per CTA of each compiled shape = the larger of the passes that use it
+  auto bytes_of = [&](int B, int G, int M) {
+    size_t b = 0;
+    if (s->block == B && s->group == G && s->minb == M) b = s->layout.total * G + s->smem_extra;
+    if (s->two_pass && s->block2 == B && s->group2 == G && s->minb2 == M) { const size_t b2 = s->layout2.total * G + s->smem_extra; b = b2 > b ? b2 : b; }
+    return (int)b;
+  };
+  bool found = false;
+#define X(B, G, M) { const int bytes = bytes_of(B, G, M); if (bytes > 0) { \
     CK(cudaFuncSetAttribute(k_run<B, G, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); \
     if (s->carveout >= 0) CK(cudaFuncSetAttribute(k_run<B, G, M>, cudaFuncAttributePreferredSharedMemoryCarveout, s->carveout)); \
-    int per_sm = 0; \
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_run<B, G, M>, B * G, bytes)); \
-    s->resident_ctas = (per_sm > 0 ? per_sm : 1) * s->n_sm; \
-    return 0; }
+    if (s->block == B && s->group == G && s->minb == M) { \
+      int per_sm = 0; \
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_run<B, G, M>, B * G, s->layout.total * G + s->smem_extra)); \
+      s->resident_ctas = (per_sm > 0 ? per_sm : 1) * s->n_sm; found = true; } \
+    if (s->two_pass && s->block2 == B && s->group2 == G && s->minb2 == M) { \
+      int per_sm = 0; \
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_run<B, G, M>, B * G, s->layout2.total * G + s->smem_extra)); \
+      s->resident_ctas2 = (per_sm > 0 ? per_sm : 1) * s->n_sm; } } }
   RS_VARIANTS(X)
 #undef X
-  return fail(RS_ERR_INVALID, "unsupported RESCO_B200_BLOCK / RESCO_B200_GROUP / RESCO_B200_REGCAP combination");
+  if (!found) return fail(RS_ERR_INVALID, "unsupported RESCO_B200_BLOCK / RESCO_B200_GROUP / RESCO_B200_REGCAP combination");
+  return 0;
 }
 
 extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, uint64_t seed, RsSim** out) {
@@ -1046,6 +1107,7 @@ extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, ui
   RsSim* s = new RsSim();
   s->device = device; s->launches = 0; s->timed = false; s->n_pairs_alloc = 0;
   s->pending = false; s->pend_obs = nullptr; s->pend_rew = nullptr; s->ev_done = nullptr;
+  s->d_frap = nullptr; s->frap_pairs = 0; s->graph = nullptr; s->graph_policy = 0; s->graph_seed = 0; s->use_wave_tables = 0;
   static_cast<RsScenario&>(s->d.sc) = *sc; s->d.n_env = n_env; s->d.seed = seed; s->d.first_env_id = 0;
   DevScenario& d = s->d.sc;
   const int L = sc->n_lanes, K = sc->n_links, S = sc->n_signals;
@@ -1190,6 +1252,8 @@ extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, ui
   const char* er = getenv("RESCO_B200_REGCAP");
   const char* eg = getenv("RESCO_B200_GROUP");
   const char* es = getenv("RESCO_B200_SINGLE");   // 1 / 0 force the single-buffer tile on / off; default: automatic
+  const char* egm = getenv("RESCO_B200_GMEM");    // 1: one pass with the whole store in the global-memory workspace
+  const char* etl = getenv("RESCO_B200_TILE");    // vehicles in the fast pass's tile (overrides RsScenario.tile_vcap)
   const size_t optin = (size_t)prop.sharedMemPerBlockOptin;
   // largest compiled instances-per-CTA shape whose tiles fit the opt-in shared memory of one CTA
   auto fit_group = [&](size_t tile, int want) {
@@ -1197,15 +1261,31 @@ extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, ui
     while (g > 1 && tile * g > optin) g = g > 8 ? 8 : (g > 4 ? g - 1 : g / 2);
     return g;
   };
-  s->d.sc.tile_single = 0;
+  // ---- the vehicle store and the tile ----
+  // `vcap` is the capacity of an instance's store in HBM (what SUMO does not have: keep it generous).  The env-step
+  // kernel works on a TILE of the store: the fast pass holds `tile` vehicles per instance in shared memory, sized for
+  // the traffic the map carries when it flows (about 1/24 of its jam capacity; cologne8: 128 vehicles, eight
+  // instances per CTA).  An instance that outgrows the tile -- a jammed network -- is not truncated: the fast pass
+  // leaves it untouched and the OVERFLOW PASS, the same kernel with the tile in a global-memory workspace (L2
+  // resident) and room for the whole store, redoes its step.  Results do not depend on the tile size.
+  const int store = sc->vcap;
+  double jam = 0;
+  for (int l = 0; l < L; ++l) if (!sc->lane_internal[l]) jam += floor(sc->lane_len[l] / 7.5) + 1.0;
+  const bool force_gmem = egm && atoi(egm) != 0;
+  int tile = etl ? atoi(etl) : sc->tile_vcap;
+  if (tile <= 0) { tile = ((int)(jam / 24.0) + 31) / 32 * 32; tile = tile < 64 ? 64 : (tile > 1024 ? 1024 : tile); }
+  tile = (tile + 3) / 4 * 4;
+  if (tile > store || force_gmem) tile = store;
+  s->d.sc.tile_cap = tile; s->d.sc.tile_single = 0; s->d.sc.tile_gmem = 0;
+  s->d.from_list = 0; s->d.overflow_count = nullptr; s->d.overflow_list = nullptr; s->d.workspace = nullptr;
   s->layout = make_layout(s->d.sc);
   s->group = fit_group(s->layout.total, eg ? atoi(eg) : 8);
   s->minb = 1;
   // Big tiles (one or two instances per SM with the ping-pong tile): keep ONE tile buffer and run the per-tick
-  // re-sort through registers (needs vcap <= 2 x 512 threads).  Half the shared memory per instance doubles the
+  // re-sort through registers (needs tile <= 2 x 512 threads).  Half the shared memory per instance doubles the
   // instances resident per SM, which is what hides the barrier waits of the plan phase on the big maps.
-  const bool single_ok = sc->vcap <= 1024;
-  const bool single = (eb && atoi(eb) < 512) ? false : (es ? (atoi(es) != 0 && single_ok) : (single_ok && s->group <= 2));
+  const bool single_ok = tile <= 1024;
+  const bool single = force_gmem ? false : ((eb && atoi(eb) < 512) ? false : (es ? (atoi(es) != 0 && single_ok) : (single_ok && s->group <= 2)));
   if (single) {
     s->d.sc.tile_single = 1;
     s->layout = make_layout(s->d.sc);
@@ -1216,9 +1296,18 @@ extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, ui
     s->group = fit_group(s->layout.total, eg ? atoi(eg) : (two_ctas ? 1 : 2));
     if (s->group == 1 && two_ctas) s->minb = 2;
   }
+  // a tile that does not fit one CTA's shared memory at all (or RESCO_B200_GMEM=1): single pass out of the workspace
+  const bool gmem = force_gmem || s->layout.total > optin;
+  if (gmem) {
+    s->d.sc.tile_single = 0; s->d.sc.tile_gmem = 1;
+    s->layout = make_layout(s->d.sc);
+    const bool two_ctas = 2 * (s->layout.total + 1024) <= (size_t)prop.sharedMemPerMultiprocessor;
+    s->group = eg ? fit_group(s->layout.total, atoi(eg)) : 1;
+    s->minb = (s->group == 1 && two_ctas) ? 2 : 1;
+  }
   if (s->layout.total > optin) {
     char buf[256];
-    snprintf(buf, sizeof buf, "rs_create: instance tile needs %zu B shared memory (> %zu B per CTA); lower vcap",
+    snprintf(buf, sizeof buf, "rs_create: the per-lane tables of one instance need %zu B shared memory (> %zu B per CTA)",
              s->layout.total, optin);
     rs_destroy(s);
     return fail(RS_ERR_CAPACITY, buf);
@@ -1227,24 +1316,50 @@ extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, ui
   // 512 threads per instance, four times 128, instead of leaving the SM with two warps (measured on a B200,
   // ingolstadt21 2048 instances vcap 1024: 64 -> 126 k, 256 -> 283 k, 512 -> 404 k, 1024 -> 375 k env steps/s;
   // grid4x4 2 x 256 -> 363 k, 2 x 512 -> 377 k; cologne8 8 x 64 -> 3.55 M, 8 x 128 -> 2.53 M)
-  s->block = eb ? atoi(eb) : (s->group >= 5 ? 64 : (s->group == 4 ? 128 : 512));
+  s->block = eb ? atoi(eb) : (gmem ? 512 : (s->group >= 5 ? 64 : (s->group == 4 ? 128 : 512)));
   if (er) s->minb = atoi(er) != 0 ? 1024 / (s->block * s->group) : 1;
-  if (s->d.sc.tile_single && (s->block < 512 || sc->vcap > 2 * s->block)) {
+  if (s->d.sc.tile_single && (s->block < 512 || tile > 2 * s->block)) {
     rs_destroy(s);
-    return fail(RS_ERR_INVALID, "rs_create: the single-buffer tile needs vcap <= 2 x threads per instance");
+    return fail(RS_ERR_INVALID, "rs_create: the single-buffer tile needs tile_vcap <= 2 x threads per instance");
   }
   const char* ep = getenv("RESCO_B200_PERSIST");
   s->d.persistent = ep ? atoi(ep) : 1;
   const char* et = getenv("RESCO_B200_TMA");
   s->d.use_tma = et ? atoi(et) : 1;
   s->n_sm = prop.multiProcessorCount;
-  TRY(dev_alloc(s, s->d.work_counter, 1));
+  TRY(dev_alloc(s, s->counters, 4));
+  s->d.work_counter = s->counters;
   TRY(dev_alloc(s, s->d.phase_clocks, 24));
   const char* ec = getenv("RESCO_B200_CARVEOUT");
   s->carveout = ec ? atoi(ec) : -1;
   const char* ex = getenv("RESCO_B200_SMEM_EXTRA");
   s->smem_extra = ex ? atoi(ex) : 0;
+  // ---- the overflow pass (only when the fast pass's tile is smaller than the store) ----
+  s->two_pass = !gmem && tile < store;
+  s->block2 = 512; s->group2 = 1; s->minb2 = 1;
+  if (s->two_pass) {
+    s->d.persistent = 1;
+    DevScenario sc2 = s->d.sc;
+    sc2.tile_cap = store; sc2.tile_single = 0; sc2.tile_gmem = 1;
+    s->layout2 = make_layout(sc2);
+    if (s->layout2.total > optin) { rs_destroy(s); return fail(RS_ERR_CAPACITY, "rs_create: per-lane tables exceed the shared memory of one CTA"); }
+    s->minb2 = 2 * (s->layout2.total + 1024) <= (size_t)prop.sharedMemPerMultiprocessor ? 2 : 1;
+    TRY(dev_alloc(s, s->d.overflow_list, N));
+    s->d.overflow_count = s->counters + 2;
+  }
   TRY(configure(s));
+  {
+    int grid = (n_env + s->group - 1) / s->group;
+    if (s->resident_ctas < grid) grid = s->resident_ctas;
+    if (gmem) {
+      s->d.persistent = 1;   // the workspace is sized for the resident grid
+      TRY(dev_alloc(s, s->d.workspace, (size_t)grid * s->group * s->layout.veh_total));
+    }
+    if (s->two_pass) {
+      int grid2 = n_env < s->resident_ctas2 ? n_env : s->resident_ctas2;
+      TRY(dev_alloc(s, s->workspace2, (size_t)grid2 * s->layout2.veh_total));
+    }
+  }
   CK(cudaEventCreate(&s->ev0)); CK(cudaEventCreate(&s->ev1));
   CK(cudaEventCreateWithFlags(&s->ev_done, cudaEventDisableTiming));
   *out = s;
@@ -1261,6 +1376,7 @@ extern "C" int rs_destroy(RsSim* s) {
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   if (s->ev_done) cudaEventDestroy(s->ev_done);
+  if (s->graph) cudaGraphExecDestroy(s->graph);
   delete s;
   return 0;
 }
@@ -1269,6 +1385,7 @@ extern "C" int rs_reset(RsSim* s, uint64_t seed, int64_t first_env_id, void* str
   if (!s) return fail(RS_ERR_INVALID, "rs_reset: null sim");
   CK(cudaSetDevice(s->device));
   s->d.seed = seed; s->d.first_env_id = first_env_id;
+  s->graph_policy = 0;   // the captured kernels carry the old seed
   k_reset<<<s->d.n_env, 64, 0, (cudaStream_t)stream>>>(s->d);
   s->launches += 1;
   CK(cudaGetLastError());
@@ -1376,6 +1493,108 @@ extern "C" int rs_policy_maxpressure(RsSim* s, const int32_t* h_pairs, int32_t n
   k_policy<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(s->d, s->d_pairs, n_pairs, s->d_valid, use_wave, outp);
   s->launches += 1;
   CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int rs_frap_load(RsSim* s, const RsFrapParams* p, const int32_t* h_pairs, int32_t n_pairs, const int32_t* h_order) {
+  if (!s || !p || !h_pairs || !h_order || n_pairs < 2 || n_pairs > kFrapMaxPairs) return fail(RS_ERR_INVALID, "rs_frap_load: bad arguments");
+  CK(cudaSetDevice(s->device));
+  const int S = s->d.sc.n_signals;
+  std::vector<float> w(FP_TOTAL);
+  struct { int off; const float* src; int n; } parts[] = {
+      {FP_P, p->p_weight, 8}, {FP_DW, p->d_weight, 4}, {FP_DB, p->d_bias, 4}, {FP_LEW, p->lane_embedding_weight, 128},
+      {FP_LEB, p->lane_embedding_bias, 16}, {FP_LCW, p->lane_conv_weight, 640}, {FP_LCB, p->lane_conv_bias, 20},
+      {FP_REW, p->relation_embedding_weight, 8}, {FP_RCW, p->relation_conv_weight, 80}, {FP_RCB, p->relation_conv_bias, 20},
+      {FP_HLW, p->hidden_layer_weight, 400}, {FP_HLB, p->hidden_layer_bias, 20}, {FP_BMW, p->before_merge_weight, 20},
+      {FP_BMB, p->before_merge_bias, 1}};
+  for (auto& q : parts) { if (!q.src) return fail(RS_ERR_INVALID, "rs_frap_load: null parameter tensor"); memcpy(w.data() + q.off, q.src, sizeof(float) * q.n); }
+  // competition mask (agents/mplight.py:19-31): pair i and the j-th OTHER pair share exactly one movement
+  std::vector<uint8_t> comp((size_t)n_pairs * (n_pairs - 1), 0);
+  for (int i = 0; i < n_pairs; ++i) {
+    int cnt = 0;
+    for (int j = 0; j < n_pairs; ++j) {
+      if (i == j) continue;
+      int v[4] = {h_pairs[2 * i], h_pairs[2 * i + 1], h_pairs[2 * j], h_pairs[2 * j + 1]}, uniq = 0;
+      for (int a = 0; a < 4; ++a) { bool dup = false; for (int b = 0; b < a; ++b) dup |= v[b] == v[a]; uniq += !dup; }
+      comp[(size_t)i * (n_pairs - 1) + cnt++] = uniq == 3;
+    }
+  }
+  for (int q = 0; q < 2 * n_pairs; ++q) if (h_pairs[q] < 0 || h_pairs[q] >= RS_N_MOVEMENTS) return fail(RS_ERR_INVALID, "rs_frap_load: movement index out of range");
+  if (!s->d_frap || s->frap_pairs != n_pairs) {
+    TRY(dev_alloc(s, s->d_frap, FP_TOTAL)); TRY(dev_alloc(s, s->d_frap_pairs, (size_t)n_pairs * 2));
+    TRY(dev_alloc(s, s->d_frap_comp, comp.size())); TRY(dev_alloc(s, s->d_frap_order, (size_t)S * n_pairs * 2));
+    s->frap_pairs = n_pairs;
+    CK(cudaFuncSetAttribute(k_policy_frap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)frap_smem_bytes(n_pairs)));
+  }
+  CK(cudaMemcpy(s->d_frap, w.data(), sizeof(float) * FP_TOTAL, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(s->d_frap_pairs, h_pairs, sizeof(int32_t) * n_pairs * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(s->d_frap_comp, comp.data(), comp.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(s->d_frap_order, h_order, sizeof(int32_t) * S * n_pairs * 2, cudaMemcpyHostToDevice));
+  s->graph_policy = 0;
+  return 0;
+}
+
+static int launch_frap(RsSim* s, const float* d_obs, int n_env_rows, int32_t* d_actions_out, float* d_q_out, cudaStream_t st) {
+  const int S = s->d.sc.n_signals, n = s->frap_pairs;
+  const int rows = (d_obs ? n_env_rows : s->d.n_env) * S;
+  const int R = kFrapThreads / n;
+  k_policy_frap<<<(rows + R - 1) / R, kFrapThreads, frap_smem_bytes(n), st>>>(d_obs ? d_obs : s->d.mplight, rows, S, s->d_frap,
+      s->d_frap_pairs, n, s->d_frap_comp, s->d_frap_order, d_q_out, d_actions_out ? d_actions_out : s->d_actions);
+  s->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int rs_policy_frap(RsSim* s, const float* d_obs, int32_t n_env_rows, int32_t* d_actions_out, float* d_q_out, void* stream) {
+  if (!s || !s->d_frap || (d_obs && n_env_rows <= 0)) return fail(RS_ERR_INVALID, "rs_policy_frap: bad arguments (rs_frap_load first)");
+  return launch_frap(s, d_obs, n_env_rows, d_actions_out, d_q_out, (cudaStream_t)stream);
+}
+
+extern "C" int rs_policy_random(RsSim* s, uint64_t seed, int32_t* d_actions_out, void* stream) {
+  if (!s) return fail(RS_ERR_INVALID, "rs_policy_random: null sim");
+  const int total = s->d.n_env * s->d.sc.n_signals;
+  if (total == 0) return 0;
+  k_policy_random<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(s->d, seed, d_actions_out ? d_actions_out : s->d_actions);
+  s->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// policy kernel + fused env step captured once into a CUDA graph and replayed: one launch per agent step
+extern "C" int rs_env_step_policy(RsSim* s, int32_t policy, uint64_t policy_seed, void* stream) {
+  if (!s || policy < RS_POLICY_MAXPRESSURE || policy > RS_POLICY_RANDOM) return fail(RS_ERR_INVALID, "rs_env_step_policy: bad arguments");
+  if ((policy == RS_POLICY_MAXPRESSURE || policy == RS_POLICY_MAXWAVE) && !s->n_pairs_alloc)
+    return fail(RS_ERR_INVALID, "rs_env_step_policy: upload the action tables with one rs_policy_maxpressure call first");
+  if (policy == RS_POLICY_FRAP && !s->d_frap) return fail(RS_ERR_INVALID, "rs_env_step_policy: rs_frap_load first");
+  CK(cudaSetDevice(s->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (s->graph_policy != policy || s->graph_seed != policy_seed) {
+    if (s->graph) { cudaGraphExecDestroy(s->graph); s->graph = nullptr; }
+    cudaStream_t cap;
+    CK(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+    CK(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+    const DevScenario& sc = s->d.sc;
+    const int total = s->d.n_env * sc.n_signals;
+    int r = 0;
+    if (policy == RS_POLICY_FRAP) r = launch_frap(s, nullptr, 0, nullptr, nullptr, cap);
+    else if (policy == RS_POLICY_RANDOM) { k_policy_random<<<(total + 127) / 128, 128, 0, cap>>>(s->d, policy_seed, s->d_actions); s->launches += 1; }
+    else { k_policy<<<(total + 127) / 128, 128, 0, cap>>>(s->d, s->d_pairs, s->n_pairs_alloc, s->d_valid, policy == RS_POLICY_MAXWAVE, s->d_actions); s->launches += 1; }
+    RunArgs a{s->d_actions, 1, sc.yellow_length, 1, sc.step_length - sc.yellow_length, 1};
+    if (!r) r = run(s, a, cap);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(cap, &g);
+    cudaStreamDestroy(cap);
+    if (r) { if (g) cudaGraphDestroy(g); return r; }
+    if (e != cudaSuccess) return fail(RS_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&s->graph, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(RS_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    s->graph_policy = policy; s->graph_seed = policy_seed;
+  } else s->launches += 2;
+  CK(cudaEventRecord(s->ev0, st));
+  CK(cudaGraphLaunch(s->graph, st));
+  CK(cudaEventRecord(s->ev1, st));
+  s->timed = true;
   return 0;
 }
 
@@ -1501,6 +1720,7 @@ extern "C" int rs_select_outputs(RsSim* s, int32_t mask) {
   if ((mask & RS_OUT_DRQ_NORM) && !s->d.drq_norm) TRY(dev_alloc(s, s->d.drq_norm, N * SL * 5));
   if ((mask & RS_OUT_MPLIGHT_FULL) && !s->d.mplight_full) TRY(dev_alloc(s, s->d.mplight_full, N * S * 49));
   s->d.out_mask = mask;
+  s->graph_policy = 0;
   return 0;
 }
 
@@ -1542,7 +1762,23 @@ extern "C" int rs_get_launch_shape(RsSim* s, int32_t* threads_per_instance, int3
   if (instances_per_cta) *instances_per_cta = s->group;
   if (grid_ctas) *grid_ctas = grid;
   if (smem_bytes_per_cta) *smem_bytes_per_cta = (int32_t)(s->layout.total * s->group);
-  if (tile_buffers) *tile_buffers = s->d.sc.tile_single ? 1 : 2;
+  if (tile_buffers) *tile_buffers = s->d.sc.tile_gmem ? 0 : (s->d.sc.tile_single ? 1 : 2);   // 0: tile in the global workspace
+  return 0;
+}
+
+extern "C" int rs_get_tile_info(RsSim* s, int32_t* tile_vcap, int32_t* store_vcap, int32_t* has_overflow_pass, int32_t* last_deferred) {
+  if (!s) return fail(RS_ERR_INVALID, "rs_get_tile_info: null sim");
+  if (tile_vcap) *tile_vcap = s->d.sc.tile_cap;
+  if (store_vcap) *store_vcap = s->d.sc.vcap;
+  if (has_overflow_pass) *has_overflow_pass = s->two_pass ? 1 : 0;
+  if (last_deferred) {
+    *last_deferred = 0;
+    if (s->two_pass) {
+      CK(cudaSetDevice(s->device));
+      CK(cudaDeviceSynchronize());
+      CK(cudaMemcpy(last_deferred, s->counters + 2, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    }
+  }
   return 0;
 }
 

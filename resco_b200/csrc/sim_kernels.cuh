@@ -74,7 +74,12 @@ struct DevScenario : RsScenario {                    // base-class pointers are 
   // choose_link() tabulated: [n_route_steps][8] = encode_nextlink code of the link a vehicle at route step s takes
   // from lane index j of that step's edge (0xFE route ends, 0xFD the lane does not lead on)
   const uint8_t* route_step_link;
+  int32_t tile_cap;      // vehicles the tile of THIS launch holds (<= vcap; vcap stays the stride of the HBM store).  A
+                         // launch whose tile is smaller than the store defers an instance that outgrows it to the
+                         // overflow pass (DevSim::overflow_*), which runs it again from the untouched HBM state
   int32_t tile_single;   // one tile buffer in shared memory (see SmemLayout::single)
+  int32_t tile_gmem;     // the vehicle tile and the per-vehicle scratch live in a per-CTA global-memory workspace (L2
+                         // resident) instead of shared memory: vehicle stores larger than one CTA's shared memory
 };
 
 // Device copy of the scenario + per-sim buffers.
@@ -102,6 +107,10 @@ struct DevSim {
   float* mplight_full;    // [N][S][49] optional
   int32_t out_mask;       // RS_OUT_* bits
   int32_t* work_counter;  // dynamic instance scheduler of the persistent launch
+  unsigned char* workspace;   // tile_gmem: [grid CTAs x instances per CTA][SmemLayout::veh_total] bytes
+  int32_t* overflow_count;    // instances the fast pass deferred (tile outgrown); null: this launch does not defer
+  int32_t* overflow_list;     // [N] their local ids
+  int32_t from_list;          // this launch IS the overflow pass: instance ids come from overflow_list[0 .. *overflow_count)
   unsigned long long* phase_clocks;   // [24] diagnostics (RS_PHASE_CLOCKS builds)
   int32_t persistent;
   int32_t use_tma;        // stage the tile with cp.async.bulk (TMA 1-D bulk copies) instead of LDG/STG

@@ -12,6 +12,8 @@ Extra keyword arguments (all optional) select the batched mode:
            (``state_fn.batched`` / ``reward_fn.batched``) and ``done`` as a bool.
   device   CUDA device index;   seed   base RNG seed of episode 1, +1 per reset (None -> the run index: episodes differ
            from each other like ``--random`` runs but repeat from one process to the next)
+  vcap     vehicles an instance's store holds (0: from the map's size);  tile_vcap  vehicles of an instance the kernel
+           keeps in shared memory (performance only, see RsScenario.tile_vcap)
   backend  factory ``Marshalled -> simulator`` (tests inject the CPU oracle); the default is the CUDA
            ``VecSim`` and raises if the extension or a GPU is missing -- there is no CPU fallback.
 """
@@ -71,7 +73,7 @@ class MultiSignal(_EnvBase):
                  libsumo=False, warmup=0, gymma=False, *, n_env: int = 1, device: int = 0,
                  seed: Optional[int] = None, backend: Optional[Callable[[Marshalled], object]] = None,
                  scenario: Optional[Scenario] = None, vcap: int = 0, sigma: float = -1.0, speed_dev: float = -1.0,
-                 tripinfo: Optional[bool] = None):
+                 tripinfo: Optional[bool] = None, tile_vcap: int = 0):
         if warmup != 0:
             raise NotImplementedError("warmup ticks before program installation are not supported (all shipped maps use 0)")
         if step_ratio != 1:
@@ -97,7 +99,7 @@ class MultiSignal(_EnvBase):
         self.tripinfo = (self.n_env == 1 and log_dir is not None) if tripinfo is None else bool(tripinfo)
         self.marshalled = marshal(sc, step_length=step_length, yellow_length=yellow_length,
                                   max_distance=float(max_distance), end_time=float(end_time), vcap=vcap,
-                                  sigma=sigma, speed_dev=speed_dev, record_trips=self.tripinfo)
+                                  sigma=sigma, speed_dev=speed_dev, record_trips=self.tripinfo, tile_vcap=tile_vcap)
         m = self.marshalled
         self.sim = (backend or _default_backend(self.n_env, device))(m)
         outs = tuple(getattr(state_fn, 'kernel_outputs', ())) + tuple(getattr(reward_fn, 'kernel_outputs', ()))

@@ -40,7 +40,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 EXPORTS = ["rs_last_error", "rs_abi_version", "rs_create", "rs_destroy", "rs_reset", "rs_set_phase", "rs_tick",
            "rs_observe", "rs_env_step", "rs_env_step_host", "rs_env_step_host_async", "rs_wait", "rs_policy_maxpressure", "rs_host_agent_wave", "rs_get_obs", "rs_get_stats",
            "rs_dump_vehicles", "rs_get_phases", "rs_get_trip_records", "rs_kernel_launches", "rs_last_step_ms", "rs_get_launch_shape",
-           "rs_select_outputs", "rs_set_host_obs"]
+           "rs_select_outputs", "rs_set_host_obs", "rs_frap_load", "rs_policy_frap", "rs_policy_random", "rs_env_step_policy",
+           "rs_get_tile_info"]
 
 
 def load_library():
@@ -75,6 +76,11 @@ def load_library():
     lib.rs_get_trip_records.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 5
     lib.rs_select_outputs.argtypes = [C.c_void_p, C.c_int32]
     lib.rs_set_host_obs.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
+    lib.rs_frap_load.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    lib.rs_policy_frap.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.rs_policy_random.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.rs_env_step_policy.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_void_p]
+    lib.rs_get_tile_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 4
     lib.rs_kernel_launches.restype = C.c_int64
     lib.rs_kernel_launches.argtypes = [C.c_void_p]
     lib.rs_last_step_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
@@ -280,6 +286,54 @@ class VecSim:
                                                         1 if use_wave else 0, self._policy_out.data_ptr(),
                                                         self._stream()))
         return self._policy_out
+
+    def load_frap(self, state_dict, pairs, valid_acts, signal_ids):
+        """Upload the FRAP Q-network of MPLight (agents/mplight.py:43-131): `state_dict` maps the reference module's
+        parameter names (p.weight, d.weight, ..., before_merge.bias) to arrays / tensors."""
+        names = ["p.weight", "d.weight", "d.bias", "lane_embedding.weight", "lane_embedding.bias", "lane_conv.weight",
+                 "lane_conv.bias", "relation_embedding.weight", "relation_conv.weight", "relation_conv.bias",
+                 "hidden_layer.weight", "hidden_layer.bias", "before_merge.weight", "before_merge.bias"]
+        keep = [np.ascontiguousarray(np.asarray(state_dict[n].detach().cpu() if hasattr(state_dict[n], "detach") else state_dict[n],
+                                                np.float32).reshape(-1)) for n in names]
+        params = (C.c_void_p * len(names))(*[k.ctypes.data for k in keep])
+        pr, order, npairs = policy_tables(pairs, valid_acts, signal_ids)
+        _check(self.lib, self.lib.rs_frap_load(self._h, params, pr.ctypes.data, npairs, order.ctypes.data))
+        self._frap_pairs = npairs
+
+    def policy_frap(self, obs=None, want_q: bool = False):
+        """Greedy MPLight actions: FRAP forward over `obs` ([n, S, 13] CUDA float tensor; default: this sim's own
+        states.mplight) -> actions [n, S] int32 (and Q-values [n, S, n_pairs] with want_q)."""
+        t = self._torch
+        n = self.n_env if obs is None else int(obs.shape[0])
+        dev = f"cuda:{self.device}"
+        if obs is not None:
+            obs = obs.to(dtype=t.float32).contiguous()
+        acts = t.empty((n, self.S), dtype=t.int32, device=dev)
+        q = t.empty((n, self.S, self._frap_pairs), dtype=t.float32, device=dev) if want_q else None
+        _check(self.lib, self.lib.rs_policy_frap(self._h, obs.data_ptr() if obs is not None else None, n, acts.data_ptr(),
+                                                 q.data_ptr() if want_q else None, self._stream()))
+        return (acts, q) if want_q else acts
+
+    def policy_random(self, seed: int = 0):
+        """Uniform random green phase per (instance, signal) -> [N, S] int32 CUDA tensor."""
+        t = self._torch
+        if getattr(self, "_rand_out", None) is None:
+            self._rand_out = t.zeros((self.n_env, self.S), dtype=t.int32, device=f"cuda:{self.device}")
+        _check(self.lib, self.lib.rs_policy_random(self._h, seed, self._rand_out.data_ptr(), self._stream()))
+        return self._rand_out
+
+    POLICIES = {"maxpressure": 1, "maxwave": 2, "frap": 3, "random": 4}
+
+    def env_step_policy(self, policy: str, seed: int = 0):
+        """policy kernel + fused env step as ONE CUDA-graph launch (the tables of the policy must have been uploaded by
+        one ordinary policy_* / load_frap call)."""
+        _check(self.lib, self.lib.rs_env_step_policy(self._h, self.POLICIES[policy], seed, self._stream()))
+
+    def tile_info(self, with_deferred: bool = True) -> dict:
+        v = [C.c_int32(0) for _ in range(4)]
+        _check(self.lib, self.lib.rs_get_tile_info(self._h, C.byref(v[0]), C.byref(v[1]), C.byref(v[2]),
+                                                   C.byref(v[3]) if with_deferred else None))
+        return dict(tile_vcap=v[0].value, store_vcap=v[1].value, overflow_pass=bool(v[2].value), last_deferred=v[3].value)
 
     # results -----------------------------------------------------------------------------------
     def obs_view(self) -> Dict[str, object]:

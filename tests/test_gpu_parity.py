@@ -24,35 +24,42 @@ def _pair(map_name, n_env, **kw):
     return sc, m, g, o
 
 
-@pytest.mark.parametrize("map_name,n_env,steps,vcap", [("cologne1", 3, 120, 0), ("cologne8", 4, 120, 0), ("grid4x4", 2, 90, 0),
+@pytest.mark.parametrize("map_name,n_env,steps,tile", [("cologne1", 3, 120, 0), ("cologne8", 4, 120, 0), ("grid4x4", 2, 90, 0),
                                                         ("ingolstadt21", 2, 60, 0), ("cologne3", 2, 60, 0),
-                                                        # the launch shape bench.py times (C2): vcap 128 -> k_run<64, 8, 1>,
-                                                        # 19 instances = two full groups of 8 and a ragged one
+                                                        # the launch shape bench.py times (C2): 128-vehicle tile ->
+                                                        # k_run<64, 8, 1>; 19 instances = two full groups of 8 and a
+                                                        # ragged one; cyclic actions jam the map, so instances outgrow
+                                                        # the tile and go through the overflow pass
                                                         ("cologne8", 19, 120, 128)])
-def test_env_step_parity_cyclic(map_name, n_env, steps, vcap):
-    sc, m, g, o = _pair(map_name, n_env, vcap=vcap)
-    if vcap == 128:
+def test_env_step_parity_cyclic(map_name, n_env, steps, tile):
+    sc, m, g, o = _pair(map_name, n_env, tile_vcap=tile)
+    deferred = 0
+    if tile == 128:
         shape = g.launch_shape()
         assert (shape["threads_per_instance"], shape["instances_per_cta"]) == (64, 8), shape
+        assert g.tile_info()["overflow_pass"]
     g.observe(); o.observe()
     util.assert_same_obs(g.obs(), o.obs(), "reset observe")
     for step in range(steps):
         act = util.cyclic_actions(m, n_env, step)
         g.env_step(act); o.env_step(act)
         util.assert_same_obs(g.obs(), o.obs(), f"{map_name} step {step}")
+        deferred += g.tile_info()["last_deferred"]
         if step % 10 == 9 or step == steps - 1:
             for e in range(n_env):
                 util.assert_same_state(g, o, e, f"{map_name} step {step} env {e}")
     sg, so = g.stats(), o.stats()
     util.assert_same_stats(sg, so, map_name)
     assert (sg["anomalies"] == 0).all() and (sg["n_cap_refused"] == 0).all()
+    if tile == 128:
+        assert deferred > 0 and sg["n_active"].max() > 128      # the overflow pass really ran
 
 
-@pytest.mark.parametrize("vcap,n_env", [(0, 2), (128, 9)])
-def test_full_episode_maxpressure_cologne8(vcap, n_env):
-    """BASELINE config C2 (cologne8 / MaxPressure), whole 360-step episode; vcap 128 is the tile bench.py times
+@pytest.mark.parametrize("tile,n_env", [(0, 2), (128, 9)])
+def test_full_episode_maxpressure_cologne8(tile, n_env):
+    """BASELINE config C2 (cologne8 / MaxPressure), whole 360-step episode; 128 vehicles is the tile bench.py times
     (k_run<64, 8, 1>: nine instances = one full group of eight and a ragged one)."""
-    sc, m, g, o = _pair("cologne8", n_env, vcap=vcap)
+    sc, m, g, o = _pair("cologne8", n_env, tile_vcap=tile)
     g.observe(); o.observe()
     nsteps = m.struct.end_tick // m.struct.step_length
     for step in range(nsteps):
@@ -67,7 +74,7 @@ def test_full_episode_maxpressure_cologne8(vcap, n_env):
         util.assert_same_state(g, o, e, f"end env {e}")
     sg, so = g.stats(), o.stats()
     util.assert_same_stats(sg, so, "episode end")
-    assert (sg["n_cap_refused"] == 0).all()      # the 128-vehicle tile never refused an insertion
+    assert (sg["n_cap_refused"] == 0).all()      # nothing was truncated (instances beyond the tile: overflow pass)
     n = sg["n_arrived"] + sg["n_active"]
     delay = (sg["sum_delay_arrived"] + sg["sum_delay_running"]) / n
     # statistical anchor (not parity): reference MAXPRESSURE cologne8 first-episode 28.76 s, mean 47.73 s
@@ -166,14 +173,14 @@ def test_synthetic_grid_parity():
 
 
 def test_full_size_batch_all_instances():
-    """BASELINE configs[1] at FULL size (cologne8 / MaxPressure / 4096 lock-step instances, the 128-vehicle tile and the
+    """BASELINE configs[1] at FULL size (cologne8 / MaxPressure / 4096 lock-step instances, the 128-vehicle tile and
     launch shape bench.py times): EVERY instance against the oracle -- observations, rewards, metrics and episode
     statistics of all 4096, per-vehicle state of a sample --, plus the size-independent properties: vehicle
     conservation, zero ordering anomalies, zero capacity refusals, instances keyed by their global id (the oracle runs
     them in a different grouping), and a second run reproducing the first bit for bit."""
     from pyoracle import OracleSim
     from resco_b200.sim import VecSim
-    sc, m = util.marshal_map("cologne8", vcap=128)
+    sc, m = util.marshal_map("cologne8", tile_vcap=128)
     N, steps = 4096, 40
     pairs, va, sig = sc.meta["phase_pairs"], sc.meta["valid_acts"], m.info["signal_ids"]
 
@@ -319,3 +326,59 @@ def test_batched_states_from_the_kernel_match_dict_view(map_name, key, rkey):
     callables the reference's goldens pin, on instances 0 and 2 of a 3-instance CUDA batch."""
     from test_multi_signal_host import batched_vs_dict
     batched_vs_dict(map_name, key, rkey, None)
+
+
+@pytest.mark.parametrize("map_name,tile,forced,policy", [("cologne8", 0, True, "cyclic"), ("cologne8", 32, False, "maxpressure"),
+                                                         ("ingolstadt21", 256, False, "cyclic")])
+def test_store_larger_than_the_tile(map_name, tile, forced, policy, monkeypatch):
+    """The vehicle store is not bounded by one CTA's shared memory.  (a) RESCO_B200_GMEM=1: the whole store lives in the
+    per-CTA global-memory workspace (launch shape tile_buffers == 0); (b) / (c) a shared-memory tile far smaller than
+    the traffic (32 vehicles on cologne8, 256 on ingolstadt21): most instances outgrow it and are stepped by the
+    overflow pass.  Same kernel, bit-identical results, nothing refused."""
+    if forced:
+        monkeypatch.setenv("RESCO_B200_GMEM", "1")
+    n_env = 11
+    sc, m, g, o = _pair(map_name, n_env, tile_vcap=tile)
+    info = g.tile_info()
+    if forced:
+        assert g.launch_shape()["tile_buffers"] == 0 and not info["overflow_pass"]
+    else:
+        assert info["overflow_pass"] and info["tile_vcap"] == tile and info["store_vcap"] > tile
+    g.observe(); o.observe()
+    deferred = 0
+    for step in range(60):
+        act = util.cyclic_actions(m, n_env, step) if policy == "cyclic" else util.maxpressure_actions(sc, m, o.obs()["mplight"])
+        g.env_step(act); o.env_step(act)
+        util.assert_same_obs(g.obs(), o.obs(), f"{map_name} step {step}")
+        deferred += g.tile_info()["last_deferred"]
+    for e in range(n_env):
+        util.assert_same_state(g, o, e, f"{map_name} env {e}")
+    sg = g.stats()
+    util.assert_same_stats(sg, o.stats(), map_name)
+    assert (sg["n_cap_refused"] == 0).all()
+    if not forced:
+        assert deferred > n_env and sg["n_active"].max() > tile
+
+
+def test_synthetic_sweep_top_rate_is_not_truncated():
+    """C5 at its top rate (1200 veh/h per entry lane, far above what the signals can serve): with a vehicle store of 8192
+    the instance is never full -- the demand that does not fit queues OUTSIDE the network as SUMO's insertion backlog
+    (departDelay), because the entry lanes are physically full, not because the store is."""
+    from pyoracle import OracleSim
+    from resco_b200.abi import marshal
+    from resco_b200.scenario.synth import synth_demand
+    from resco_b200.sim import VecSim
+    sc = util.load("grid4x4")
+    m = marshal(sc, step_length=10, yellow_length=3, synthetic=synth_demand(sc, 1200), vcap=8192)
+    n_env = 3
+    g = VecSim(m, n_env, seed=5); o = OracleSim(m, n_env, seed=5)
+    g.reset(5, 0); o.reset(5, 0)
+    g.observe(); o.observe()
+    assert g.tile_info()["store_vcap"] == 8192
+    for step in range(120):
+        act = g.policy_maxpressure(sc.meta["phase_pairs"], sc.meta["valid_acts"], m.info["signal_ids"]).cpu().numpy()
+        g.env_step(act); o.env_step(act)
+    util.assert_same_obs(g.obs(), o.obs(), "top rate")
+    sg = g.stats()
+    util.assert_same_stats(sg, o.stats(), "top rate")
+    assert (sg["n_cap_refused"] == 0).all() and (sg["n_backlog"] > 0).all() and (sg["n_active"] > 1024).all(), sg
