@@ -1,22 +1,31 @@
 #!/usr/bin/env python
 """bench.py -- env steps/sec of the hot path (BASELINE.json metric) on N GPUs of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c3|c4|c5]
 
-Workload (config.workload): BASELINE.json configs[1] -- cologne8 (8 signals), MaxPressure agent,
-4096 lock-step environment instances per GPU ("weak" scaling: per-GPU work is fixed).  One "step" =
-one MultiSignal.step() of every instance = batched MaxPressure action selection + step_length (10)
-one-second simulation ticks + Signal.observe + states.mplight + rewards (multi_signal.py:164-197).
-Demand is the map's own 2046-trip table replicated to every instance (synthetic in the sense that
-per-instance driver randomness -- speedFactor, dawdling -- is drawn from Philox keyed by the
-global instance id); "data": "synthetic".
+Workloads (BASELINE.json `configs`; `--config`, default c2 = the configuration the metric is quoted on):
 
-`value`  : device-timed (CUDA events on the launching stream), actions/obs resident in HBM.
-`e2e`    : the same metric through the host-buffer C-ABI call (rs_env_step_host) with the batched
-           host agent: H2D of actions + D2H of obs/reward inside the timed region.
-`--impl reference`: the CPU arm.  The reference's own CPU path (MultiSignal over libsumo) cannot
-           run anywhere in this environment (SUMO is not installed), so this arm times
-           the CPU oracle port of the same algorithm on all host cores (cpu_baseline.kind = "port").
+  c2  cologne8 (8 signals) / MaxPressure / 4096 lock-step instances per GPU; states.mplight + rewards.wait
+  c3  ingolstadt21 (21 signals) / IDQN / 8192 instances: the kernel emits states.drq_norm + rewards.wait_norm and
+      rewards.pressure every step (agent_config.py:83-94 and BASELINE's wording); IDQN's own network is pfrl code on the
+      caller's side, so actions are its epsilon = 1 exploration: uniform random green phases drawn on the device
+  c4  ingolstadt21 / MPLight shared controller / 8192 instances per GPU (65536 on 8): states.mplight of every rank is
+      all-gathered over NCCL, rank 0 evaluates FRAP (agents/mplight.py, random-init weights: no checkpoints here) for
+      all instances and broadcasts the actions; two half-batches per rank on two streams, so the collectives of one
+      half overlap the env-step kernel of the other
+  c5  synthetic 4x4 grid, Poisson (Bernoulli per tick) demand swept over 300 / 600 / 900 / 1200 veh/h per entry lane,
+      16384 instances per GPU, MaxPressure; `value` is the sweep total, per-rate lines in config.sweep
+
+One "step" = one MultiSignal.step() of every instance = batched policy + step_length one-second simulation ticks +
+Signal.observe + states + rewards (multi_signal.py:164-197), issued as ONE CUDA-graph launch (rs_env_step_policy).
+Per-instance driver randomness (speedFactor, dawdling) is Philox keyed by the global instance id; "data": "synthetic".
+
+`value`  : device-timed (CUDA events on the launching stream), actions / observations resident in HBM.
+`e2e`    : the same metric through the host-buffer C-ABI call (rs_env_step_host[_async]): pinned H2D of the actions +
+           D2H of the observation and reward inside the timed region, host-side agent.
+`--impl reference`: the CPU arm.  The reference's own CPU path (MultiSignal over libsumo) cannot run anywhere in this
+           environment (SUMO is not installed), so this arm times the CPU oracle port of the same
+           algorithm on all host cores (cpu_baseline.kind = "port").
 """
 from __future__ import annotations
 
@@ -34,12 +43,27 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-MAP = "cologne8"
-N_ENV_PER_GPU = 4096
-VCAP = 128   # cologne8/MaxPressure peaks at ~110 concurrent vehicles per instance (32-seed CPU check); a full tile only delays insertions
+CONFIGS = {
+    "c2": dict(map="cologne8", n_env=4096, policy="maxpressure", tile=128, vcap=0, rates=[0.0], preroll=90,
+               host_obs="mplight", reward_kind=0, outputs=(),
+               what="cologne8 (8 signals) / MaxPressure / {n} lock-step instances per GPU"),
+    "c3": dict(map="ingolstadt21", n_env=8192, policy="random", tile=0, vcap=0, rates=[0.0], preroll=60,
+               host_obs="drq_norm", reward_kind=1, outputs=("drq_norm",),
+               what="ingolstadt21 (21 signals) / IDQN (epsilon = 1: uniform random actions on the device) / {n} instances "
+                    "per GPU / kernel emits drq_norm + wait_norm + pressure"),
+    "c4": dict(map="ingolstadt21", n_env=8192, policy="frap", tile=0, vcap=0, rates=[0.0], preroll=60,
+               host_obs="mplight", reward_kind=2, outputs=(),
+               what="ingolstadt21 / MPLight shared controller (FRAP forward on rank 0 over the NCCL all-gathered "
+                    "states.mplight, actions broadcast) / {n} instances per GPU"),
+    "c5": dict(map="grid4x4", n_env=16384, policy="maxpressure", tile=4096, vcap=4096, rates=[300.0, 600.0, 900.0, 1200.0],
+               preroll=60, host_obs="mplight", reward_kind=0, outputs=(),
+               what="synthetic 4x4 grid / Bernoulli-per-tick demand sweep 300-1200 veh/h per entry lane / MaxPressure / "
+                    "{n} instances per GPU"),
+}
+MAP = CONFIGS["c2"]["map"]
 
 
-def _marshal(map_name=MAP, vcap=VCAP, synthetic_rate=0.0):
+def _marshal(map_name, vcap=0, tile=0, synthetic_rate=0.0):
     from resco_b200.abi import marshal
     from resco_b200.scenario import Scenario
     sc = Scenario.load(os.path.join(ROOT, "resco_b200", "data", map_name + ".npz"))
@@ -49,73 +73,102 @@ def _marshal(map_name=MAP, vcap=VCAP, synthetic_rate=0.0):
         from resco_b200.scenario.synth import synth_demand
         synth = synth_demand(sc, synthetic_rate)
     m = marshal(sc, step_length=mc["step_length"], yellow_length=mc["yellow_length"], max_distance=200.0, vcap=vcap,
-                synthetic=synth)
+                tile_vcap=tile, synthetic=synth)
     return sc, m
 
 
-def host_maxpressure(sc, m):
-    """Batched MAXPRESSURE agent over host observation buffers (agents/maxpressure.py + maxwave.py:18-38): the
-    library's host-side agent front-end (rs_host_agent_wave)."""
-    from resco_b200.sim import HostWaveAgent
-    return HostWaveAgent(sc.meta["phase_pairs"], sc.meta["valid_acts"], m.info["signal_ids"])
+def frap_state_dict(n_pairs, seed=0):
+    """Random-init FRAP parameters (no checkpoints in this environment), PyTorch default initialisers, fixed seed."""
+    import torch
+    from resco_b200.agents import BatchedFRAP
+    g = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    model = BatchedFRAP([[0, 1]] * n_pairs)
+    del g
+    return {k: v.detach().clone() for k, v in model.state_dict().items()}, model
 
 
-def numpy_maxpressure(sc, m):
-    """The same agent in numpy (CPU-baseline workers: the oracle arm must not depend on the CUDA library)."""
+def numpy_wave_agent(sc, m):
+    """MAXPRESSURE in numpy (CPU-baseline workers: the oracle arm must not depend on the CUDA library)."""
     pairs = np.asarray(sc.meta["phase_pairs"], np.int64)
     va = sc.meta["valid_acts"]
-    sig = m.info["signal_ids"]
     tables = []
-    for s in sig:
+    for s in m.info["signal_ids"]:
         idxs = list(range(len(pairs))) if va is None else [int(k) for k in va[s].keys()]
         acts = idxs if va is None else [va[s][str(k)] for k in idxs]
         tables.append((pairs[idxs, 0] + 1, pairs[idxs, 1] + 1, np.asarray(acts, np.int32)))
 
-    def act(mplight):
+    def act(obs):
+        mplight = obs["mplight"]
         out = np.empty(mplight.shape[:2], np.int32)
         for i, (p0, p1, acts) in enumerate(tables):
-            press = mplight[:, i, p0] + mplight[:, i, p1]
-            out[:, i] = acts[np.argmax(press, 1)]
+            out[:, i] = acts[np.argmax(mplight[:, i, p0] + mplight[:, i, p1], 1)]
         return out
     return act
 
 
+def host_agent(cfg, sc, m, n_env, seed):
+    """The caller's act() for the CPU arm and for the e2e loop: observation batch in host memory -> [n, S] actions."""
+    sig = m.info["signal_ids"]
+    if cfg["policy"] == "maxpressure":
+        return numpy_wave_agent(sc, m)
+    ng = np.asarray([len(m.info["green_states"][s]) for s in sig], np.int64)
+    if cfg["policy"] == "random":
+        rng = np.random.default_rng(seed)
+        return lambda obs: (rng.integers(0, 1 << 30, (n_env, len(sig))) % ng[None, :]).astype(np.int32)
+    import torch
+    torch.set_num_threads(1)
+    sd, _ = frap_state_dict(len(sc.meta["phase_pairs"]))
+    from resco_b200.agents import BatchedFRAP
+    model = BatchedFRAP(sc.meta["phase_pairs"])
+    model.load_state_dict(sd)
+    va = sc.meta["valid_acts"]
+    return lambda obs: model.act(torch.from_numpy(obs["mplight"]), va, sig).numpy().astype(np.int32)
+
+
 # ------------------------------------------------------------------------------------------------
 def _cpu_worker(args):
-    """One process = one core: `n_inst` oracle instances, `warm` untimed + `n_steps` timed env steps with MaxPressure."""
-    n_inst, n_steps, seed, first, warm = args
+    """One process = one core: `n_inst` oracle instances, `warm` untimed + `n_steps` timed env steps of the config."""
+    key, n_inst, n_steps, seed, first, warm, rate = args
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     from pyoracle import OracleSim
-    sc, m = _marshal()
-    agent = numpy_maxpressure(sc, m)
+    cfg = CONFIGS[key]
+    sc, m = _marshal(cfg["map"], cfg["vcap"], 0, rate)
+    agent = host_agent(cfg, sc, m, n_inst, seed + first)
     sim = OracleSim(m, n_inst, seed=seed)
     sim.reset(seed, first)
     sim.observe()
     for _ in range(warm):
-        sim.env_step(agent(sim.obs()["mplight"]))
+        sim.env_step(agent(sim.obs()))
     t0 = time.perf_counter()
     for _ in range(n_steps):
-        sim.env_step(agent(sim.obs()["mplight"]))
+        sim.env_step(agent(sim.obs()))
     return time.perf_counter() - t0, n_inst * n_steps
 
 
-def cpu_baseline(n_steps=120, n_inst=32, cores=None, warm=90):
-    """Oracle port on the host cores, bounded sample (about 10-30 s of CPU work in total): every core steps its own
-    `n_inst` instances `n_steps` env steps after `warm` untimed ones (the GPU arm's pre-roll: both arms time the loaded network)."""
+def cpu_baseline(key="c2", n_steps=120, n_inst=None, cores=None, warm=None):
+    """Oracle port on the host cores, bounded sample (about 10-30 s of CPU work): every core steps its own `n_inst`
+    instances `n_steps` env steps after `warm` untimed ones (the GPU arm's pre-roll: both arms time the loaded network)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyoracle
     pyoracle.build()
+    pyoracle.lib()          # dlopen liboracle.so in THIS process too: the forked workers inherit the mapping
+    cfg = CONFIGS[key]
     cores = cores or os.cpu_count() or 1
+    warm = cfg["preroll"] if warm is None else warm
+    n_inst = n_inst or {"c2": 32, "c3": 4, "c4": 4, "c5": 4}[key]
     n_steps = max(1, min(int(n_steps), 355 - warm))      # one episode is 360 env steps
+    rate = cfg["rates"][len(cfg["rates"]) // 2]
     t0 = time.perf_counter()
     with mp.get_context("fork").Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(n_inst, n_steps, 1, c * n_inst, warm) for c in range(cores)])
+        res = pool.map(_cpu_worker, [(key, n_inst, n_steps, 1, c * n_inst, warm, rate) for c in range(cores)])
     wall = time.perf_counter() - t0
     busy = max(r[0] for r in res)
     total = sum(r[1] for r in res)
     return dict(value=total / busy, unit="env steps/s", cores=cores, kind="port",
-                sample=f"{cores} procs x {n_inst} cologne8 instances x {n_steps} env steps (MaxPressure, after {warm} untimed "
-                       f"steps), oracle/microsim.c, max-over-procs busy time {busy:.2f}s (wall {wall:.2f}s)")
+                sample=f"{cores} procs x {n_inst} {cfg['map']} instances x {n_steps} env steps ({cfg['policy']}"
+                       + (f", synthetic {rate:g} veh/h/lane" if rate > 0 else "") + f", after {warm} untimed steps), "
+                       f"oracle/microsim.c, max-over-procs busy time {busy:.2f}s (wall {wall:.2f}s)")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -165,60 +218,44 @@ class ClockSampler:
                     reasons=sorted(reasons), samples=len(sm))
 
 
-def algorithmic_bytes_per_step(m, vbar):
-    """SURVEY.md §8(d): B_step = T*B_tick + L_in*20 + S*(obs_dim*4+4),
+def algorithmic_bytes_per_step(m, vbar, obs_floats_per_signal=13):
+    """SURVEY.md section 8(d): B_step = T*B_tick + L_in*20 + S*(obs_dim*4+4),
     B_tick = V*(24R+16W) + L*(8R+8W) + S*(8R+8W) + K*1R."""
     st = m.struct
     n_tl_links = int(sum(len(p[0][1]) for p in m.info["programs_installed"].values()))
     b_tick = vbar * 40.0 + st.n_lanes * 16.0 + st.n_signals * 16.0 + n_tl_links
-    return st.step_length * b_tick + st.n_sig_lanes * 20.0 + st.n_signals * (13 * 4 + 4)
+    return st.step_length * b_tick + st.n_sig_lanes * 20.0 + st.n_signals * (obs_floats_per_signal * 4 + 4)
 
 
+def kernel_counters(key):
+    """ncu-derived per-launch counters of the config's dominant kernel (profiles/kernel_counters.json, written from the
+    committed ncu captures by tools/ncu_counters.py): DRAM bytes and executed warp instructions per env step."""
+    p = os.path.join(ROOT, "profiles", "kernel_counters.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(key)
+    return None
+
+
+# ------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from resco_b200.sim import VecSim, build_library
+    from resco_b200.sim import HostWaveAgent, VecSim, build_library
+    cfg = CONFIGS[args.config]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        dist.init_process_group("nccl", device_id=torch.device(dev))
     if not os.path.exists(os.path.join(ROOT, "resco_b200", "csrc", "libresco_b200.so")):
         build_library()
-    sc, m = _marshal(args.map, args.vcap, args.synthetic_rate)
-    n_env = args.n_env
-    sim = VecSim(m, n_env, seed=args.seed, device=local)
-    sim.reset(args.seed, rank * n_env)
-    sim.observe()
-    pairs, va, sig = sc.meta["phase_pairs"], sc.meta["valid_acts"], m.info["signal_ids"]
-    flush = torch.empty(160 << 20, dtype=torch.uint8, device=f"cuda:{local}")
+    n_env = args.n_env or cfg["n_env"]
+    policy = cfg["policy"]
+    shared = args.config == "c4"
+    flush = torch.empty(160 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
-    gather_buf = None
-    if args.allgather and world > 1:
-        gather_buf = torch.empty((world,) + tuple(sim.obs_view()["mplight"].shape), device=f"cuda:{local}")
-
-    def one_step():
-        act = sim.policy_maxpressure(pairs, va, sig)
-        sim.env_step(act)
-        if gather_buf is not None:      # shared-policy configs (C4): obs all-gather over NVLink
-            dist.all_gather_into_tensor(gather_buf, sim.obs_view()["mplight"])
-
-    episode_steps = m.struct.end_tick // m.struct.step_length
-    state = {"step": 0}
-
-    def preroll():
-        # untimed set-up: reset and run the episode up to a loaded network before anything is timed
-        sim.reset(args.seed, rank * n_env)
-        sim.observe()
-        for _ in range(args.preroll):
-            act = sim.policy_maxpressure(pairs, va, sig)
-            sim.env_step(act)
-        state["step"] = args.preroll
-
-    def ensure_room():
-        if state["step"] + 1 > episode_steps:
-            preroll()
 
     def barrier():
         torch.cuda.synchronize()
@@ -226,149 +263,274 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    preroll()
-    for _ in range(args.warmup):
-        ensure_room(); one_step(); state["step"] += 1
-    barrier()
-    st0 = sim.stats()
+    def make_sim(sc, m, count, first):
+        sim = VecSim(m, count, seed=args.seed, device=local)
+        if cfg["outputs"]:
+            sim.select_outputs(*cfg["outputs"])
+        sim.reset(args.seed, first)
+        sim.observe()
+        pairs, va, sig = sc.meta["phase_pairs"], sc.meta["valid_acts"], m.info["signal_ids"]
+        if policy == "maxpressure":
+            sim.policy_maxpressure(pairs, va, sig)         # uploads the action tables
+        elif policy == "frap":
+            sim.load_frap(frap_state_dict(len(pairs))[0], pairs, va, sig)
+        return sim
+
+    sweep = []
+    clocks = None
+    tot_steps, tot_ms = 0, 0.0
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kern_ms = []
-    barrier()
-    wall0 = time.perf_counter()
-    for i in range(args.steps):
-        ensure_room()
-        flush.zero_()                       # evict the instance tiles from L2 between timed steps (untimed)
-        ev[i][0].record(stream)
-        one_step()
-        ev[i][1].record(stream)
-        state["step"] += 1
-        if i % 16 == 15:
+    last = None
+    for rate in cfg["rates"]:
+        sc, m = _marshal(cfg["map"], cfg["vcap"], cfg["tile"] if args.tile < 0 else args.tile, rate)
+        episode_steps = m.struct.end_tick // m.struct.step_length
+        S = m.struct.n_signals
+        if shared:       # two half-batches per rank on two streams: the collectives of one overlap the kernel of the other
+            n_a = n_env // 2
+            parts = [(0, n_a), (n_a, n_env - n_a)]
+            streams = [torch.cuda.Stream(device=local), torch.cuda.Stream(device=local)]
+        else:
+            parts = [(0, n_env)]
+            streams = [stream]
+        sims = [make_sim(sc, m, cnt, rank * n_env + first) for first, cnt in parts]
+        gather = [torch.empty((world * cnt, S, 13), device=dev) for _, cnt in parts] if shared and world > 1 else None
+        acts_all = [torch.empty((world * cnt, S), dtype=torch.int32, device=dev) for _, cnt in parts] if shared else None
+        state = {"step": 0}
+
+        def one_step():
+            if not shared:
+                sims[0].env_step_policy(policy, seed=args.seed)
+                return
+            for h, (sim, st) in enumerate(zip(sims, streams)):
+                with torch.cuda.stream(st):
+                    cnt = parts[h][1]
+                    if world > 1:      # configs[3]: obs all-gather over NVLink, shared policy on rank 0, actions broadcast
+                        dist.all_gather_into_tensor(gather[h], sim.obs_view()["mplight"])
+                        if rank == 0:
+                            acts_all[h].copy_(sim.policy_frap(gather[h]))
+                        dist.broadcast(acts_all[h], src=0)
+                        sim.env_step(acts_all[h][rank * cnt:(rank + 1) * cnt])
+                    else:
+                        sim.env_step(sim.policy_frap())
+
+        def preroll():
+            # untimed set-up: reset and run the episode up to a loaded network before anything is timed
+            for h, sim in enumerate(sims):
+                sim.reset(args.seed, rank * n_env + parts[h][0])
+                sim.observe()
+            for _ in range(cfg["preroll"] if args.preroll < 0 else args.preroll):
+                one_step()
             torch.cuda.synchronize()
-            kern_ms.append(sim.last_step_ms())
-    barrier()
-    wall = time.perf_counter() - wall0
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    clocks = sampler.stop() if rank == 0 else None
-    launches = args.steps * 2   # per timed step: k_policy + k_run (pre-roll/reset launches are untimed set-up)
-    st1 = sim.stats()
-    t = torch.tensor([dev_ms], dtype=torch.float64, device=f"cuda:{local}")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms_max = float(t.item())
-    total_env = n_env * world
-    value = total_env * args.steps / (dev_ms_max / 1e3)
+            state["step"] = cfg["preroll"] if args.preroll < 0 else args.preroll
 
-    # ---- end-to-end through the host-buffer C-ABI call + host agent ----
-    agent = host_maxpressure(sc, m)
-    obs_h = sim.obs()["mplight"]
-    e2e_steps = max(8, min(args.steps, 100))
-    if state["step"] + e2e_steps + 3 > episode_steps:
+        def ensure_room():
+            if state["step"] + 1 > episode_steps:
+                preroll()
+
         preroll()
-        obs_h = sim.obs()["mplight"]
-    for _ in range(3):
-        obs_h, _ = sim.env_step_host(agent(obs_h), reward_kind=0)
-    barrier()
-    e2e_t = 0.0
-    for _ in range(e2e_steps):
-        flush.zero_()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        obs_h, rew_h = sim.env_step_host(agent(obs_h), reward_kind=0)
-        e2e_t += time.perf_counter() - t0
-    te = torch.tensor([e2e_t], dtype=torch.float64, device=f"cuda:{local}")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_sync_value = total_env * e2e_steps / float(te.item())
+        for _ in range(args.warmup):
+            ensure_room(); one_step(); state["step"] += 1
+        barrier()
+        st0 = [s.stats() for s in sims]
+        if rank == 0 and rate == cfg["rates"][0]:
+            sampler.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        kern_ms, deferred, redone = [], 0, 0
+        barrier()
+        wall0 = time.perf_counter()
+        for i in range(args.steps):
+            ensure_room()
+            flush.zero_()                       # evict the instance tiles from L2 between timed steps (untimed)
+            ev[i][0].record(stream)
+            for st in streams:
+                if st is not stream:
+                    st.wait_event(ev[i][0])
+            one_step()
+            for st in streams:
+                if st is not stream:
+                    stream.wait_stream(st)
+            ev[i][1].record(stream)
+            state["step"] += 1
+            if not shared and (i % 4 == 3 or i == args.steps - 1):
+                torch.cuda.synchronize()        # every 4th step: kernel time of the graph launch + deferred-instance count
+                kern_ms.append(sims[0].last_step_ms())
+                ti = sims[0].tile_info()
+                deferred, redone = max(deferred, ti["last_deferred"]), max(redone, ti["last_redone"])
+        barrier()
+        wall = time.perf_counter() - wall0
+        dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+        st1 = [s.stats() for s in sims]
+        t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms_max = float(t.item())
+        ticks = int(st1[0]["tick"][0] - st0[0]["tick"][0])
+        act_ticks = sum(float((b["sum_active_ticks"].astype(np.float64) - a["sum_active_ticks"]).sum()) for a, b in zip(st0, st1))
+        vbar = act_ticks / max(ticks, 1) / n_env
+        refused = int(sum(int((b["n_cap_refused"] - a["n_cap_refused"]).sum()) for a, b in zip(st0, st1)))
+        sweep.append(dict(rate_veh_h_lane=rate, value=n_env * world * args.steps / (dev_ms_max / 1e3),
+                          ms_per_step=dev_ms_max / args.steps, vbar_active_vehicles=vbar, n_cap_refused=refused,
+                          max_redone_in_cta_per_step=redone, max_deferred_to_overflow_pass_per_step=deferred, backlog_mean=float(np.mean(np.concatenate([b["n_backlog"] for b in st1]))),
+                          kernel_ms=float(np.mean(kern_ms)) if kern_ms else None, wall_s=wall))
+        tot_steps += args.steps
+        tot_ms += dev_ms_max
+        last = (sc, m, sims, streams, parts, vbar, kern_ms, S)
+        if rate != cfg["rates"][-1]:
+            for s in sims:
+                s.close()
+    clocks = sampler.stop() if rank == 0 else None
+    sc, m, sims, streams, parts, vbar, kern_ms, S = last
+    total_env = n_env * world
+    value = total_env * tot_steps / (tot_ms / 1e3)
+    refused_total = sum(x["n_cap_refused"] for x in sweep)
+    shape = sims[0].launch_shape()
+    tile = sims[0].tile_info(with_deferred=False)
 
-    # ---- the same loop double-buffered: two sims hold half of the rank's instances each and are stepped
-    #      alternately (rs_env_step_host_async / rs_wait), so the host agent of one half overlaps the device
-    #      step of the other.  Same instances (global ids), same agent, same bytes over PCIe per env step. ----
+    # ---- end-to-end through the host-buffer C-ABI call + host agent: two sims holding half of the rank's instances
+    #      each, stepped alternately (rs_env_step_host_async / rs_wait), so the host agent of one half overlaps the
+    #      device step of the other.  Same instances (global ids), same bytes over PCIe per env step. ----
+    for s in sims:
+        s.close()
     n_a = n_env // 2
-    halves, streams = [], [torch.cuda.Stream(device=local), torch.cuda.Stream(device=local)]
-    for first, cnt in ((0, n_a), (n_a, n_env - n_a)):
-        h = VecSim(m, cnt, seed=args.seed, device=local)
-        h.reset(args.seed, rank * n_env + first)
-        h.observe()
-        for _ in range(args.preroll):
-            h.env_step(h.policy_maxpressure(pairs, va, sig))
+    hparts = [(0, n_a), (n_a, n_env - n_a)]
+    hstreams = [torch.cuda.Stream(device=local), torch.cuda.Stream(device=local)]
+    halves = []
+    if policy == "maxpressure":
+        hagent = HostWaveAgent(sc.meta["phase_pairs"], sc.meta["valid_acts"], m.info["signal_ids"])
+        hact = [lambda obs: hagent(obs)] * 2
+    elif policy == "random":
+        rngs = [np.random.default_rng(args.seed + rank * 2 + k) for k in range(2)]
+        ng = np.asarray([len(m.info["green_states"][s]) for s in m.info["signal_ids"]], np.int64)
+        hact = [(lambda obs, r=r, c=c: (r.integers(0, 1 << 30, (c, S)) % ng[None, :]).astype(np.int32)) for r, (_, c) in zip(rngs, hparts)]
+    else:
+        hact = None     # MPLight: the shared policy runs on the device; the host only reads the reward back
+    for first, cnt in hparts:
+        h = make_sim(sc, m, cnt, rank * n_env + first)
+        h.set_host_obs(cfg["host_obs"])
+        pre = cfg["preroll"] if args.preroll < 0 else args.preroll
+        for _ in range(pre):
+            h.env_step_policy(policy, seed=args.seed) if policy != "frap" else h.env_step(h.policy_frap())
         halves.append(h)
+    torch.cuda.synchronize()
+    episode_steps = m.struct.end_tick // m.struct.step_length
+    pre = cfg["preroll"] if args.preroll < 0 else args.preroll
     pipe_warm = 3
-    pipe_steps = max(8, min(args.steps, episode_steps - args.preroll - pipe_warm - 2))
-    obs_half = [h.obs()["mplight"] for h in halves]
-    for _ in range(pipe_warm):           # untimed: first calls allocate the page-locked host buffers of the two halves
-        for hi, (h, st) in enumerate(zip(halves, streams)):
-            h.env_step_host_async(agent(obs_half[hi]), reward_kind=0, stream=st)
+    pipe_steps = max(4, min(args.steps, 100, episode_steps - pre - pipe_warm - 2))
+    rk = cfg["reward_kind"]
+    obs_bytes = int(np.prod(halves[0]._host_obs_shape[1:])) * 4 * n_env
+    if hact is not None:
+        obs_half = [None, None]
+        for hi, (h, st) in enumerate(zip(halves, hstreams)):
+            h.env_step_host_async(hact[hi](h.obs()[cfg["host_obs"]]), reward_kind=rk, stream=st)
         obs_half = [h.wait()[0] for h in halves]
-    barrier()
-    t0 = time.perf_counter()
-    for h, st, o in zip(halves, streams, obs_half):            # prime: one step in flight per half
-        h.env_step_host_async(agent(o), reward_kind=0, stream=st)
-    for _ in range(pipe_steps - 1):
-        with torch.cuda.stream(streams[0]):
-            flush.zero_()                                       # L2 eviction once per iteration, INSIDE the timed region
-            fl = streams[0].record_event()
-        streams[1].wait_event(fl)
-        for h, st in zip(halves, streams):
-            o, _ = h.wait()
-            h.env_step_host_async(agent(o), reward_kind=0, stream=st)
-    for h in halves:
-        h.wait()
-    e2e_t = time.perf_counter() - t0
-    te = torch.tensor([e2e_t], dtype=torch.float64, device=f"cuda:{local}")
+        for _ in range(pipe_warm - 1):
+            for hi, (h, st) in enumerate(zip(halves, hstreams)):
+                h.env_step_host_async(hact[hi](obs_half[hi]), reward_kind=rk, stream=st)
+            obs_half = [h.wait()[0] for h in halves]
+        barrier()
+        t0 = time.perf_counter()
+        for hi, (h, st) in enumerate(zip(halves, hstreams)):        # prime: one step in flight per half
+            h.env_step_host_async(hact[hi](obs_half[hi]), reward_kind=rk, stream=st)
+        for _ in range(pipe_steps - 1):
+            with torch.cuda.stream(hstreams[0]):
+                flush.zero_()                                       # L2 eviction once per iteration, INSIDE the timed region
+                fl = hstreams[0].record_event()
+            hstreams[1].wait_event(fl)
+            for hi, (h, st) in enumerate(zip(halves, hstreams)):
+                o, _ = h.wait()
+                h.env_step_host_async(hact[hi](o), reward_kind=rk, stream=st)
+        for h in halves:
+            h.wait()
+        e2e_t = time.perf_counter() - t0
+        e2e = dict(h2d_bytes_per_step=n_env * S * 4, d2h_bytes_per_step=obs_bytes + n_env * S * 4,
+                   mode="2 half-batch sims double-buffered on 2 streams (rs_env_step_host_async / rs_wait), host agent "
+                        f"({policy}) on the returned {cfg['host_obs']} observation, L2 flush inside the timed region")
+    else:
+        rew_host = [torch.empty((cnt, S), dtype=torch.float32).pin_memory() for _, cnt in hparts]
+        key_r = "reward_pressure"
+
+        def mp_step():
+            for hi, (h, st) in enumerate(zip(halves, hstreams)):
+                with torch.cuda.stream(st):
+                    h.env_step(h.policy_frap())
+                    rew_host[hi].copy_(h.obs_view()[key_r], non_blocking=True)
+        for _ in range(pipe_warm):
+            mp_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(pipe_steps):
+            mp_step()
+            with torch.cuda.stream(hstreams[0]):
+                flush.zero_()
+        torch.cuda.synchronize()
+        e2e_t = time.perf_counter() - t0
+        e2e = dict(h2d_bytes_per_step=0, d2h_bytes_per_step=n_env * S * 4,
+                   mode="MPLight's shared policy runs on the device (rs_policy_frap), so a step's inputs never leave HBM; "
+                        "per step: FRAP + fused env step per half-batch on 2 streams, D2H of the pressure reward into pinned "
+                        "memory, L2 flush inside the timed region")
+    te = torch.tensor([e2e_t], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = total_env * pipe_steps / float(te.item())
+    e2e.update(value=total_env * pipe_steps / float(te.item()), unit="env steps/s", steps=pipe_steps)
     for h in halves:
         h.close()
-    S = sim.S
 
     if rank == 0:
-        ticks = int(st1["tick"][0] - st0["tick"][0])
-        vbar = float((st1["sum_active_ticks"].astype(np.float64) - st0["sum_active_ticks"]).mean() / max(ticks, 1))
-        bstep = algorithmic_bytes_per_step(m, vbar)
-        k_ms = float(np.mean(kern_ms)) if kern_ms else dev_ms / args.steps
+        obs_fl = {"mplight": 13, "drq_norm": 13}[cfg["host_obs"]]
+        bstep = algorithmic_bytes_per_step(m, vbar, obs_fl)
+        ms_step = tot_ms / tot_steps
+        k_ms = float(np.mean(kern_ms)) if kern_ms else ms_step
+        k_ms = min(k_ms, ms_step)          # a kernel cannot take longer than the step that contains it
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
             peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)"
         else:
             peak = 6650.0; peak_src = "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
         achieved = bstep * n_env / (k_ms / 1e3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic_bytes_per_launch.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("k_run_env_step")
-        cb = cpu_baseline() if world == 1 and not args.no_cpu else None
+        kc = kernel_counters(args.config)
+        traffic = kc["dram_bytes_per_env_step"] * n_env if kc else None
+        issue = None
+        sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6 if clocks else 1965e6
+        if kc and kc.get("warp_insts_per_env_step"):
+            t_issue = kc["warp_insts_per_env_step"] * n_env / (148 * 4 * sm_hz) * 1e3
+            issue = dict(warp_insts_per_env_step=kc["warp_insts_per_env_step"], issue_slots_per_s=148 * 4 * sm_hz,
+                         ms_at_full_issue_rate=t_issue, frac=t_issue / k_ms, source=kc.get("source"),
+                         what="executed warp instructions of one launch / (148 SMs x 4 schedulers x SM clock) over the measured kernel time: the "
+                              "fraction of the issue-slot ceiling this instruction stream reaches")
+        cb = cpu_baseline(args.config) if world == 1 and not args.no_cpu else None
         out = {
             "metric": "env steps/sec (summed instances)", "value": value, "unit": "env steps/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.map} ({sim.S} signals) / MaxPressure / {n_env} lock-step instances per GPU"
-                                   + (f" / synthetic Bernoulli demand {args.synthetic_rate:g} veh/h/entry-lane" if args.synthetic_rate > 0 else ""),
+            "config": {"workload": cfg["what"].format(n=n_env), "name": args.config,
                        "n_env_per_gpu": n_env, "n_env_total": total_env, "sim_ticks_per_env_step": m.struct.step_length,
-                       "vcap": m.struct.vcap, **sim.launch_shape(), "persistent_grid": os.environ.get("RESCO_B200_PERSIST", "1") != "0",
+                       "vcap": m.struct.vcap, **tile, **shape,
+                       "n_cap_refused_in_timed_window": refused_total,
                        "l2": "flushed between timed steps (160 MiB memset > 126 MB L2, untimed)",
                        "timing": "per-step CUDA events on the launching stream, summed; max over ranks",
-                       "allgather_obs": bool(gather_buf is not None),
-                       "avg_delay_parity_vs_sumo": "not measurable here: SUMO/libsumo is installed neither in the build container nor on the GPU box; statistical anchors against utils/avg_timeLoss.py are in DESIGN.md section 7",
-                       "preroll_env_steps": args.preroll,
-                       "episode_window": "timed steps start after an untimed pre-roll of the episode (loaded network); the episode restarts (reset + pre-roll, untimed) when its 360 steps are used up"},
+                       "allgather_obs": bool(shared and world > 1),
+                       "avg_delay_parity_vs_sumo": "not measurable here: SUMO/libsumo is installed neither in the build container nor on the GPU box; statistical anchors against utils/avg_timeLoss.py: tests/test_anchors.py, DESIGN.md section 7",
+                       "preroll_env_steps": cfg["preroll"] if args.preroll < 0 else args.preroll,
+                       "episode_window": "timed steps start after an untimed pre-roll of the episode (loaded network); the episode restarts (reset + pre-roll, untimed) when its steps are used up",
+                       "max_redone_in_cta_per_step": max(x["max_redone_in_cta_per_step"] for x in sweep),
+                       "max_deferred_to_overflow_pass_per_step": max(x["max_deferred_to_overflow_pass_per_step"] for x in sweep),
+                       "sweep": sweep if len(sweep) > 1 else None},
             "sim_ticks_per_s": value * m.struct.step_length,
-            "e2e": {"value": e2e_value, "unit": "env steps/s", "h2d_bytes_per_step": n_env * S * 4,
-                    "d2h_bytes_per_step": n_env * S * 13 * 4 + n_env * S * 4, "steps": pipe_steps,
-                    "mode": "2 half-batch sims double-buffered on 2 streams (rs_env_step_host_async / rs_wait), host MaxPressure agent (rs_host_agent_wave), L2 flush inside the timed region",
-                    "sync_value": e2e_sync_value,
-                    "what": "per env step: pinned H2D of the actions, fused env step, D2H of mplight obs + reward, host MaxPressure agent (rs_host_agent_wave) on the returned obs; wall clock; value = double-buffered (mode), sync_value = one rs_env_step_host call per step over the whole batch"},
-            "gpu_launches": int(launches),
+            "e2e": e2e,
+            "gpu_launches": int(tot_steps * (2 + (1 if tile["overflow_pass"] else 0)) * len(parts)),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "rs::k_run<BLOCK> (fused env step)", "kernel_ms": k_ms,
+                         "traffic": traffic, "kernel": "rs::k_run (fused env step)", "kernel_ms": k_ms,
+                         "kernel_ms_source": "mean of rs_last_step_ms (CUDA events around the graph launch) over every 4th timed step, capped by ms_per_step",
                          "algorithmic_bytes_per_env_step": bstep, "vbar_active_vehicles": vbar, "peak_source": peak_src,
-                         "note": "algorithmic bytes follow SURVEY §8(d) (one tile round trip PER TICK); the fused kernel moves the tile once per env step, so DRAM traffic is far below the algorithmic count and the kernel is latency/issue bound, not HBM bound"},
-            "cpu_baseline": cb, "clocks": clocks, "wall_s": wall,
+                         "issue": issue,
+                         "note": "algorithmic bytes follow SURVEY 8(d) (one tile round trip PER TICK); the fused kernel moves the tile once per env step, so DRAM traffic is far below the algorithmic count and the kernel is latency/issue bound, not HBM bound: roofline.issue is the ceiling that binds"},
+            "cpu_baseline": cb, "clocks": clocks,
         }
+        if refused_total:
+            out["invalid"] = f"{refused_total} insertions were refused by the vehicle store in the timed window: raise vcap"
         print(json.dumps(out))
+        if refused_total:
+            sys.exit(3)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -378,17 +540,20 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cfg = CONFIGS[args.config]
     t0 = time.perf_counter()
-    # one "step" of this arm = one env step of every core's 32 instances; W warm-up steps untimed, K timed (K is capped
+    # one "step" of this arm = one env step of every core's instances; W warm-up steps untimed, K timed (K is capped
     # by the episode length: the sample stays bounded whatever K the caller passes)
-    cb = cpu_baseline(n_steps=max(args.steps, 1), n_inst=32, warm=args.preroll + max(args.warmup, 0))
+    pre = cfg["preroll"] if args.preroll < 0 else args.preroll
+    cb = cpu_baseline(args.config, n_steps=max(args.steps, 1), warm=pre + max(args.warmup, 0))
     wall = time.perf_counter() - t0
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    n_inst = {"c2": 32, "c3": 4, "c4": 4, "c5": 4}[args.config]
     out = {"impl": "reference", "metric": "env steps/sec (summed instances)", "value": cb["value"],
            "unit": "env steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": 1e3 * 32 * cb["cores"] / cb["value"], "higher_is_better": True, "scaling": "weak",
+           "ms_per_step": 1e3 * n_inst * cb["cores"] / cb["value"], "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"{MAP} (8 signals) / MaxPressure / bounded sample: 32 instances per host core",
+           "config": {"workload": cfg["what"].format(n=f"bounded sample: {n_inst} per host core;"), "name": args.config,
                       "note": "reference CPU path (MultiSignal over libsumo) unavailable: SUMO is not installed and its source is not in the reference tree; this arm is the CPU oracle port of the same algorithm (kind=port)"},
            "cpu_baseline": cb,
            "e2e": {"value": cb["value"], "unit": "env steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -399,16 +564,14 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--map", default=MAP)
-    ap.add_argument("--n-env", type=int, default=N_ENV_PER_GPU)
-    ap.add_argument("--vcap", type=int, default=VCAP)
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--n-env", type=int, default=0, help="instances per GPU (0: the config's)")
+    ap.add_argument("--tile", type=int, default=-1, help="vehicles in the shared-memory tile (-1: the config's)")
     ap.add_argument("--seed", type=int, default=1)
-    ap.add_argument("--preroll", type=int, default=90, help="untimed env steps after reset before warm-up")
-    ap.add_argument("--synthetic-rate", type=float, default=0.0, help="veh/h per entry lane (configs[4]); 0 = map's trip table")
-    ap.add_argument("--allgather", action="store_true", help="NCCL all-gather of the mplight obs every step (C4)")
+    ap.add_argument("--preroll", type=int, default=-1, help="untimed env steps after reset before warm-up (-1: the config's)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

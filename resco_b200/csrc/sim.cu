@@ -32,10 +32,10 @@ struct SmemLayout {
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-__host__ __device__ inline SmemLayout make_layout(const DevScenario& sc) {
+__host__ __device__ inline SmemLayout make_layout_ex(const DevScenario& sc, int tile_cap, int single, int gmem) {
   SmemLayout m;
-  m.single = sc.tile_single; m.gmem = sc.tile_gmem;
-  m.vcap = sc.tile_cap; m.L = sc.n_lanes; m.n_tls = sc.n_tls; m.S = sc.n_signals; m.O = sc.n_origins;
+  m.single = single; m.gmem = gmem;
+  m.vcap = tile_cap; m.L = sc.n_lanes; m.n_tls = sc.n_tls; m.S = sc.n_signals; m.O = sc.n_origins;
   m.SL = sc.n_sig_lanes; m.n_vt = sc.n_vtypes;
   size_t o = 0;
   m.off_bufA = o; o = align16(o + (size_t)kVehWords * m.vcap * 4);
@@ -72,6 +72,9 @@ __host__ __device__ inline SmemLayout make_layout(const DevScenario& sc) {
   m.total = o;
   return m;
 }
+__host__ __device__ inline SmemLayout make_layout(const DevScenario& sc) {
+  return make_layout_ex(sc, sc.tile_cap, sc.tile_single, sc.tile_gmem);
+}
 
 // Optional per-phase cycle accounting (build with -DRS_PHASE_CLOCKS=1, tools/phase_clocks.sh): thread 0 of the CTA
 // charges the cycles since the previous mark to slot i; k_run adds the CTA totals to DevSim::phase_clocks.
@@ -88,7 +91,7 @@ __shared__ long long s_pclk_last;
 enum { PC_STAGE = 0, PC_S0, PC_S1, PC_S2, PC_S3A, PC_S3B, PC_S4, PC_S5, PC_S6, PC_S7, PC_OBS, PC_WRITE, PC_SCHED, PC_N };
 
 // misc slots
-enum { M_NARR = 0, M_NOK, M_NAFTER, M_NDIRTY, M_NOKC, M_BAIL /* the instance outgrew the tile: its step is redone by the overflow pass */, M_WARP = 16 /* 32 ints of warp totals */ };
+enum { M_NARR = 0, M_NOK, M_NAFTER, M_NDIRTY, M_NOKC, M_MAYDEFER /* outgrowing the tile defers the instance instead of refusing insertions */, M_BAIL /* the instance outgrew the tile: its step is redone by the overflow pass */, M_WARP = 16 /* 32 ints of warp totals */ };
 
 constexpr int kDirty = 0x40000000;   // flag bit in cnt2[l]: the lane gained or lost a vehicle this tick
 
@@ -370,7 +373,7 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
   {
     const int n_after = misc[M_NAFTER], n_ok = misc[M_NOK];
     const bool all = n_after + n_ok <= m.vcap;
-    if (!all && D.overflow_count && !D.from_list && tid == 0) misc[M_BAIL] = 1;   // tile outgrown (not the store): defer, do not refuse
+    if (!all && misc[M_MAYDEFER] && tid == 0) misc[M_BAIL] = 1;   // tile outgrown (not the store): defer, do not refuse
     for (int j = tid; j < nokc; j += BLOCK) {
       const int o = oklist[j];
       if (cand[o].ok_dd < 0) continue;
@@ -641,10 +644,13 @@ __device__ __forceinline__ void dev_set_phase(const DevScenario& sc, Tile& T, in
   T.tls_state[t] = __ldg(sc.phase_state_off + p0 + idx);
 }
 
+// Steps one instance; returns true if the instance outgrew the tile of this run (its HBM state is then untouched).
+// `may_defer`: outgrowing the tile defers (to the in-CTA redo or the overflow list) instead of refusing insertions;
+// `to_list`: a deferred instance queues itself on the overflow list; `use_tma`: stage with bulk copies + the slot's mbarrier.
 template <int BLOCK, int G>
-__device__ __forceinline__ void run_instance(const DevSim& D, const RunArgs& A, const SmemLayout& m,
+__device__ __forceinline__ bool run_instance(const DevSim& D, const RunArgs& A, const SmemLayout& m,
                                              unsigned char* smem, unsigned char* vb, const int env, const bool real_slot,
-                                             uint32_t& tma_parity) {
+                                             uint32_t& tma_parity, const bool may_defer, const bool to_list, const bool use_tma) {
   const DevScenario& sc = D.sc;
   const int tid = threadIdx.x % BLOCK;
   uint32_t* cur = (uint32_t*)(vb + m.off_bufA);
@@ -692,8 +698,8 @@ __device__ __forceinline__ void run_instance(const DevSim& D, const RunArgs& A, 
   __syncthreads();
   int32_t* misc0 = (int32_t*)(smem + m.off_misc);
   if (tid == 0) {   // already larger than this launch's tile: defer at once and step an empty tile (barriers stay in lock-step)
-    const int big = (D.overflow_count && !D.from_list && hdr[H_NVEH] > m.vcap) ? 1 : 0;
-    misc0[M_BAIL] = big;
+    const int big = (may_defer && hdr[H_NVEH] > m.vcap) ? 1 : 0;
+    misc0[M_BAIL] = big; misc0[M_MAYDEFER] = may_defer ? 1 : 0;
     if (big) hdr[H_NVEH] = 0;
   }
   __syncthreads();
@@ -701,7 +707,7 @@ __device__ __forceinline__ void run_instance(const DevSim& D, const RunArgs& A, 
   {
     const uint32_t* g = D.veh + (size_t)env * kVehWords * sc.vcap;
     const int n4 = (n0 + 3) >> 2;
-    if (D.use_tma && !m.gmem) {   // TMA: 1-D bulk copies (one per word array) tracked by the slot's mbarrier
+    if (use_tma) {   // TMA: 1-D bulk copies (one per word array) tracked by the slot's mbarrier
       if (n4 > 0) {
         uint64_t* bar = (uint64_t*)(smem + m.off_mbar);
         if (tid == 0) {
@@ -780,12 +786,12 @@ __device__ __forceinline__ void run_instance(const DevSim& D, const RunArgs& A, 
   // ---- write the tile back; a deferred instance leaves its HBM state untouched and queues itself for the overflow
   //      pass (same barriers either way: the instances of a CTA run in lock-step) ----
   const bool bail = misc0[M_BAIL] != 0;
-  if (bail && tid == 0 && real_slot) D.overflow_list[atomicAdd(D.overflow_count, 1)] = env;
+  if (bail && to_list && tid == 0 && real_slot) D.overflow_list[atomicAdd(D.overflow_count, 1)] = env;
   {
     const int n1 = hdr[H_NVEH];
     uint32_t* g = D.veh + (size_t)env * kVehWords * sc.vcap;
     const int n4 = (n1 + 3) >> 2;
-    if (D.use_tma && !m.gmem) {   // shared -> global bulk stores; the tile may be reused once they have been READ
+    if (use_tma) {   // shared -> global bulk stores; the tile may be reused once they have been READ
       fence_proxy_async_smem();
       __syncthreads();
       if (tid == 0 && n4 > 0 && !bail) {
@@ -814,6 +820,7 @@ __device__ __forceinline__ void run_instance(const DevSim& D, const RunArgs& A, 
     }
   }
   PCLK(PC_WRITE);
+  return bail;
 }
 
 // Persistent launch: the grid holds as many CTAs as are resident at once (148 SMs x CTAs/SM); each CTA
@@ -849,7 +856,39 @@ __global__ void __launch_bounds__(TPI * G, MINB) k_run(const __grid_constant__ D
     // a slot past the end of the batch repeats the last instance (same inputs -> identical stores)
     const int slot = env0 + (int)(threadIdx.x / TPI);
     const int item = min(slot, n_work - 1);
-    run_instance<TPI, G>(D, A, m, my, vb, D.from_list ? D.overflow_list[item] : item, slot < n_work, tma_parity);
+    const int env = D.from_list ? D.overflow_list[item] : item;
+    const bool has_next = D.overflow_count != nullptr && !D.from_list;      // somebody can take what outgrows this tile
+    const bool redo = G > 1 && D.sc.redo_cap > 0;
+    const bool tma = D.use_tma && !m.gmem;
+    const bool bail = run_instance<TPI, G>(D, A, m, my, vb, env, slot < n_work, tma_parity, has_next || redo, has_next && !redo, tma);
+    if constexpr (G > 1) {
+      if (redo) {   // instances of this group that outgrew their slot: the whole CTA steps them again, one at a time
+        __shared__ int s_redo[G];
+        __shared__ int s_nredo;
+        __syncthreads();
+        if (threadIdx.x == 0) s_nredo = 0;
+        __syncthreads();
+        if (bail && slot < n_work && threadIdx.x % TPI == 0) s_redo[atomicAdd(&s_nredo, 1)] = env;
+        __syncthreads();
+        const int nr = s_nredo;
+        if (nr > 0) {   // (s_redo is static shared memory: the redo tile only overwrites the dynamic part)
+          if (threadIdx.x == 0 && D.redo_count) atomicAdd(D.redo_count, nr);
+          if (tma) { if (threadIdx.x % TPI == 0) mbar_inval((uint64_t*)(my + m.off_mbar)); }
+          __syncthreads();
+          const SmemLayout mb = make_layout_ex(D.sc, D.sc.redo_cap, D.sc.redo_single, 0);
+          uint32_t unused_parity = 0;
+          for (int r = 0; r < nr; ++r) {
+            run_instance<TPI * G, 1>(D, A, mb, smem, smem, s_redo[r], true, unused_parity, has_next, has_next, false);
+            __syncthreads();
+          }
+          if (tma) {
+            if (threadIdx.x % TPI == 0) mbar_init((uint64_t*)(my + m.off_mbar), 1);
+            tma_parity = 0;
+          }
+          __syncthreads();
+        }
+      }
+    }
     if (!D.persistent) break;
     __syncthreads();
   }
@@ -966,7 +1005,7 @@ struct RsSim {
   int resident_ctas;
   // overflow pass (see rs_create): same kernel, whole store in the global workspace, instances from overflow_list
   bool two_pass; SmemLayout layout2; int block2, group2, minb2, resident_ctas2; unsigned char* workspace2;
-  int32_t* counters;   // [0] work counter of the fast pass, [1] of the overflow pass, [2] number of deferred instances
+  int32_t* counters;   // [0] work counter of the fast pass, [1] of the overflow pass, [2] instances deferred to it, [3] redone in-CTA
   std::vector<void*> allocs;
   int64_t launches;
   cudaEvent_t ev0, ev1, ev_done;
@@ -1026,8 +1065,9 @@ static int launch_run(RsSim* s, const DevSim& d, size_t smem_per_instance, int r
 
 // (threads per instance, instances per CTA, min CTAs/SM for __launch_bounds__: 1 = registers uncapped,
 //  1024/(TPI*G) = 64 registers per thread)
-#define RS_VARIANTS(X) X(64, 1, 1) X(64, 2, 1) X(64, 4, 1) X(64, 5, 1) X(64, 6, 1) X(64, 7, 1) X(64, 8, 1) X(32, 8, 1) X(32, 16, 1) \
-  X(128, 1, 1) X(128, 2, 1) X(128, 4, 1) X(256, 1, 1) X(256, 2, 1) X(512, 1, 1) X(512, 2, 1) X(512, 1, 2)
+//  The shapes rs_create can choose (fit_group: 8, 7, 6, 5 instances of 64 threads, 4 of 128, 2 or 1 of 512); other
+//  combinations were measured in round 1 and are no longer compiled.
+#define RS_VARIANTS(X) X(64, 5, 1) X(64, 6, 1) X(64, 7, 1) X(64, 8, 1) X(128, 4, 1) X(512, 1, 1) X(512, 2, 1) X(512, 1, 2)
 
 static int launch_variant(RsSim* s, int block, int group, int minb, const DevSim& d, size_t smem_per_instance, int resident,
                           int n_work, const RunArgs& a, cudaStream_t st) {
@@ -1329,13 +1369,29 @@ extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, ui
   s->n_sm = prop.multiProcessorCount;
   TRY(dev_alloc(s, s->counters, 4));
   s->d.work_counter = s->counters;
+  s->d.redo_count = s->counters + 3;
   TRY(dev_alloc(s, s->d.phase_clocks, 24));
   const char* ec = getenv("RESCO_B200_CARVEOUT");
   s->carveout = ec ? atoi(ec) : -1;
   const char* ex = getenv("RESCO_B200_SMEM_EXTRA");
   s->smem_extra = ex ? atoi(ex) : 0;
-  // ---- the overflow pass (only when the fast pass's tile is smaller than the store) ----
-  s->two_pass = !gmem && tile < store;
+  // ---- instances that outgrow the tile ----
+  // (1) launches with several instances per CTA: the CTA that hits such an instance steps it again at once with all its
+  //     threads on a tile laid over the CTA's whole shared memory (no second launch, no tail: the other CTAs keep
+  //     pulling groups); (2) what outgrows that too -- or any tile of a one-instance-per-CTA launch -- goes on the
+  //     overflow list and is stepped by the overflow pass out of the global-memory workspace.
+  s->d.sc.redo_cap = 0; s->d.sc.redo_single = 0;
+  if (!gmem && s->group > 1 && tile < store && !(getenv("RESCO_B200_REDO") && atoi(getenv("RESCO_B200_REDO")) == 0)) {
+    const size_t cta_smem = s->layout.total * s->group;
+    const int threads = s->block * s->group;
+    const int single1 = threads >= 512 ? 1 : 0;
+    int cap = store;
+    if (single1) { cap = cap < 1024 ? cap : 1024; cap = cap < 2 * threads ? cap : 2 * threads; }
+    cap = cap / 4 * 4;
+    while (cap > tile && make_layout_ex(s->d.sc, cap, single1, 0).total > cta_smem) cap -= 32;
+    if (cap > tile) { s->d.sc.redo_cap = cap; s->d.sc.redo_single = single1; }
+  }
+  s->two_pass = !gmem && (s->d.sc.redo_cap > 0 ? s->d.sc.redo_cap : tile) < store;
   s->block2 = 512; s->group2 = 1; s->minb2 = 1;
   if (s->two_pass) {
     s->d.persistent = 1;
@@ -1766,18 +1822,20 @@ extern "C" int rs_get_launch_shape(RsSim* s, int32_t* threads_per_instance, int3
   return 0;
 }
 
-extern "C" int rs_get_tile_info(RsSim* s, int32_t* tile_vcap, int32_t* store_vcap, int32_t* has_overflow_pass, int32_t* last_deferred) {
+extern "C" int rs_get_tile_info(RsSim* s, int32_t* tile_vcap, int32_t* store_vcap, int32_t* redo_vcap, int32_t* has_overflow_pass,
+                                int32_t* last_redone, int32_t* last_deferred) {
   if (!s) return fail(RS_ERR_INVALID, "rs_get_tile_info: null sim");
   if (tile_vcap) *tile_vcap = s->d.sc.tile_cap;
   if (store_vcap) *store_vcap = s->d.sc.vcap;
+  if (redo_vcap) *redo_vcap = s->d.sc.redo_cap;
   if (has_overflow_pass) *has_overflow_pass = s->two_pass ? 1 : 0;
-  if (last_deferred) {
-    *last_deferred = 0;
-    if (s->two_pass) {
-      CK(cudaSetDevice(s->device));
-      CK(cudaDeviceSynchronize());
-      CK(cudaMemcpy(last_deferred, s->counters + 2, sizeof(int32_t), cudaMemcpyDeviceToHost));
-    }
+  if (last_redone || last_deferred) {
+    int32_t c[4] = {0, 0, 0, 0};
+    CK(cudaSetDevice(s->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(c, s->counters, sizeof c, cudaMemcpyDeviceToHost));
+    if (last_redone) *last_redone = c[3];
+    if (last_deferred) *last_deferred = c[2];
   }
   return 0;
 }

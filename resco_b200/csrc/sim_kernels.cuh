@@ -78,6 +78,10 @@ struct DevScenario : RsScenario {                    // base-class pointers are 
                          // launch whose tile is smaller than the store defers an instance that outgrows it to the
                          // overflow pass (DevSim::overflow_*), which runs it again from the untouched HBM state
   int32_t tile_single;   // one tile buffer in shared memory (see SmemLayout::single)
+  int32_t redo_cap;      // > 0 (launches with several instances per CTA): an instance that outgrows its slot's tile is
+                         // stepped again at once by the WHOLE CTA on a tile of redo_cap vehicles laid over the CTA's
+                         // shared memory (all G x TPI threads on one instance); only what outgrows that too is deferred
+  int32_t redo_single;   // the redo tile is single-buffered
   int32_t tile_gmem;     // the vehicle tile and the per-vehicle scratch live in a per-CTA global-memory workspace (L2
                          // resident) instead of shared memory: vehicle stores larger than one CTA's shared memory
 };
@@ -110,6 +114,7 @@ struct DevSim {
   unsigned char* workspace;   // tile_gmem: [grid CTAs x instances per CTA][SmemLayout::veh_total] bytes
   int32_t* overflow_count;    // instances the fast pass deferred (tile outgrown); null: this launch does not defer
   int32_t* overflow_list;     // [N] their local ids
+  int32_t* redo_count;        // instances stepped again inside their CTA (redo_cap) during this launch
   int32_t from_list;          // this launch IS the overflow pass: instance ids come from overflow_list[0 .. *overflow_count)
   unsigned long long* phase_clocks;   // [24] diagnostics (RS_PHASE_CLOCKS builds)
   int32_t persistent;
@@ -666,6 +671,9 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
 __device__ __forceinline__ void tma_store_1d(void* dst_gmem, const void* src_smem, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                :: "l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_inval(uint64_t* bar) {
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tma_store_commit_and_wait_read() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");

@@ -80,7 +80,7 @@ def load_library():
     lib.rs_policy_frap.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.rs_policy_random.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.rs_env_step_policy.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_void_p]
-    lib.rs_get_tile_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 4
+    lib.rs_get_tile_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 6
     lib.rs_kernel_launches.restype = C.c_int64
     lib.rs_kernel_launches.argtypes = [C.c_void_p]
     lib.rs_last_step_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
@@ -330,10 +330,16 @@ class VecSim:
         _check(self.lib, self.lib.rs_env_step_policy(self._h, self.POLICIES[policy], seed, self._stream()))
 
     def tile_info(self, with_deferred: bool = True) -> dict:
-        v = [C.c_int32(0) for _ in range(4)]
-        _check(self.lib, self.lib.rs_get_tile_info(self._h, C.byref(v[0]), C.byref(v[1]), C.byref(v[2]),
-                                                   C.byref(v[3]) if with_deferred else None))
-        return dict(tile_vcap=v[0].value, store_vcap=v[1].value, overflow_pass=bool(v[2].value), last_deferred=v[3].value)
+        """tile / store / in-CTA redo capacities; with_deferred: how many instances the last launch stepped again in
+        their CTA (`last_redone`) or deferred to the overflow pass (`last_deferred`) -- synchronises the device."""
+        v = [C.c_int32(0) for _ in range(6)]
+        _check(self.lib, self.lib.rs_get_tile_info(self._h, C.byref(v[0]), C.byref(v[1]), C.byref(v[2]), C.byref(v[3]),
+                                                   C.byref(v[4]) if with_deferred else None,
+                                                   C.byref(v[5]) if with_deferred else None))
+        out = dict(tile_vcap=v[0].value, store_vcap=v[1].value, redo_vcap=v[2].value, overflow_pass=bool(v[3].value))
+        if with_deferred:
+            out.update(last_redone=v[4].value, last_deferred=v[5].value)
+        return out
 
     # results -----------------------------------------------------------------------------------
     def obs_view(self) -> Dict[str, object]:

@@ -37,14 +37,16 @@ def test_env_step_parity_cyclic(map_name, n_env, steps, tile):
     if tile == 128:
         shape = g.launch_shape()
         assert (shape["threads_per_instance"], shape["instances_per_cta"]) == (64, 8), shape
-        assert g.tile_info()["overflow_pass"]
+        info = g.tile_info()
+        assert info["tile_vcap"] == 128 and info["redo_vcap"] > 128
     g.observe(); o.observe()
     util.assert_same_obs(g.obs(), o.obs(), "reset observe")
     for step in range(steps):
         act = util.cyclic_actions(m, n_env, step)
         g.env_step(act); o.env_step(act)
         util.assert_same_obs(g.obs(), o.obs(), f"{map_name} step {step}")
-        deferred += g.tile_info()["last_deferred"]
+        ti = g.tile_info()
+        deferred += ti["last_deferred"] + ti["last_redone"]
         if step % 10 == 9 or step == steps - 1:
             for e in range(n_env):
                 util.assert_same_state(g, o, e, f"{map_name} step {step} env {e}")
@@ -52,7 +54,7 @@ def test_env_step_parity_cyclic(map_name, n_env, steps, tile):
     util.assert_same_stats(sg, so, map_name)
     assert (sg["anomalies"] == 0).all() and (sg["n_cap_refused"] == 0).all()
     if tile == 128:
-        assert deferred > 0 and sg["n_active"].max() > 128      # the overflow pass really ran
+        assert deferred > 0 and sg["n_active"].max() > 128      # instances beyond the tile really were stepped again
 
 
 @pytest.mark.parametrize("tile,n_env", [(0, 2), (128, 9)])
@@ -328,36 +330,54 @@ def test_batched_states_from_the_kernel_match_dict_view(map_name, key, rkey):
     batched_vs_dict(map_name, key, rkey, None)
 
 
-@pytest.mark.parametrize("map_name,tile,forced,policy", [("cologne8", 0, True, "cyclic"), ("cologne8", 32, False, "maxpressure"),
-                                                         ("ingolstadt21", 256, False, "cyclic")])
-def test_store_larger_than_the_tile(map_name, tile, forced, policy, monkeypatch):
-    """The vehicle store is not bounded by one CTA's shared memory.  (a) RESCO_B200_GMEM=1: the whole store lives in the
-    per-CTA global-memory workspace (launch shape tile_buffers == 0); (b) / (c) a shared-memory tile far smaller than
-    the traffic (32 vehicles on cologne8, 256 on ingolstadt21): most instances outgrow it and are stepped by the
-    overflow pass.  Same kernel, bit-identical results, nothing refused."""
-    if forced:
+@pytest.mark.parametrize("map_name,tile,mode,policy", [("cologne8", 0, "gmem", "cyclic"), ("cologne8", 32, "redo", "maxpressure"),
+                                                       ("cologne8", 32, "list", "maxpressure"), ("ingolstadt21", 256, "list", "cyclic"),
+                                                       ("grid4x4", 64, "redo+list", "cyclic")])
+def test_store_larger_than_the_tile(map_name, tile, mode, policy, monkeypatch):
+    """The vehicle store is not bounded by one CTA's shared memory, and results do not depend on the tile size.
+    gmem: RESCO_B200_GMEM=1, the whole store lives in the per-CTA global-memory workspace (tile_buffers == 0).
+    redo: a 32-vehicle tile on cologne8 (eight instances per CTA): nearly every instance outgrows it and is stepped
+          again at once by its whole CTA on a tile laid over the CTA's shared memory.
+    list: the same with the in-CTA redo switched off (RESCO_B200_REDO=0), and ingolstadt21 with a 256-vehicle tile (one
+          instance per CTA): instances go on the overflow list and through the overflow pass (global workspace).
+    redo+list: grid4x4 with a 64-vehicle tile under a jamming policy: the in-CTA redo tile is outgrown too.
+    Always the same kernel and bit-identical results, nothing refused."""
+    if mode == "gmem":
         monkeypatch.setenv("RESCO_B200_GMEM", "1")
+    if mode == "list" and map_name == "cologne8":
+        monkeypatch.setenv("RESCO_B200_REDO", "0")
     n_env = 11
-    sc, m, g, o = _pair(map_name, n_env, tile_vcap=tile)
+    kw = dict(tile_vcap=tile)
+    if mode == "redo+list":
+        kw["vcap"] = 4096
+    sc, m, g, o = _pair(map_name, n_env, **kw)
     info = g.tile_info()
-    if forced:
+    if mode == "gmem":
         assert g.launch_shape()["tile_buffers"] == 0 and not info["overflow_pass"]
     else:
-        assert info["overflow_pass"] and info["tile_vcap"] == tile and info["store_vcap"] > tile
+        assert info["tile_vcap"] == tile and info["store_vcap"] > tile
+        assert (info["redo_vcap"] > tile) == ("redo" in mode) and info["overflow_pass"] == ("list" in mode), info
     g.observe(); o.observe()
-    deferred = 0
-    for step in range(60):
-        act = util.cyclic_actions(m, n_env, step) if policy == "cyclic" else util.maxpressure_actions(sc, m, o.obs()["mplight"])
+    redone = deferred = 0
+    steps = 90 if mode == "redo+list" else 60
+    for step in range(steps):
+        act = util.cyclic_actions(m, n_env, step, period=9 if mode == "redo+list" else 3) if policy == "cyclic" \
+            else util.maxpressure_actions(sc, m, o.obs()["mplight"])
         g.env_step(act); o.env_step(act)
         util.assert_same_obs(g.obs(), o.obs(), f"{map_name} step {step}")
-        deferred += g.tile_info()["last_deferred"]
+        ti = g.tile_info()
+        redone += ti["last_redone"]; deferred += ti["last_deferred"]
     for e in range(n_env):
         util.assert_same_state(g, o, e, f"{map_name} env {e}")
     sg = g.stats()
     util.assert_same_stats(sg, o.stats(), map_name)
     assert (sg["n_cap_refused"] == 0).all()
-    if not forced:
-        assert deferred > n_env and sg["n_active"].max() > tile
+    if "redo" in mode:
+        assert redone > n_env
+    if "list" in mode:
+        assert deferred > 0, (redone, deferred, sg["n_active"])
+    if mode != "gmem":
+        assert sg["n_active"].max() > tile
 
 
 def test_synthetic_sweep_top_rate_is_not_truncated():
