@@ -650,7 +650,8 @@ __device__ __forceinline__ void dev_set_phase(const DevScenario& sc, Tile& T, in
 template <int BLOCK, int G>
 __device__ __forceinline__ bool run_instance(const DevSim& D, const RunArgs& A, const SmemLayout& m,
                                              unsigned char* smem, unsigned char* vb, const int env, const bool real_slot,
-                                             uint32_t& tma_parity, const bool may_defer, const bool to_list, const bool use_tma) {
+                                             uint32_t& tma_parity, const bool may_defer, const bool to_list, const bool use_tma,
+                                             const bool skip_heavy) {
   const DevScenario& sc = D.sc;
   const int tid = threadIdx.x % BLOCK;
   uint32_t* cur = (uint32_t*)(vb + m.off_bufA);
@@ -698,7 +699,11 @@ __device__ __forceinline__ bool run_instance(const DevSim& D, const RunArgs& A, 
   __syncthreads();
   int32_t* misc0 = (int32_t*)(smem + m.off_misc);
   if (tid == 0) {   // already larger than this launch's tile: defer at once and step an empty tile (barriers stay in lock-step)
-    const int big = (may_defer && hdr[H_NVEH] > m.vcap) ? 1 : 0;
+    // skip_heavy (2): the instance is on this launch's heavy list -- it was above the heavy threshold when the previous
+    // launch wrote it back -- and the CTA that took it there either has stepped it already (launch stamp) or still is
+    const int stamp = D.heavy_count ? D.heavy_count[3] + 1 : 0;
+    const int big = (skip_heavy && (hdr[H_DONE] == stamp || hdr[H_NVEH] > m.vcap - D.heavy_margin)) ? 2
+                  : ((may_defer && hdr[H_NVEH] > m.vcap) ? 1 : 0);
     misc0[M_BAIL] = big; misc0[M_MAYDEFER] = may_defer ? 1 : 0;
     if (big) hdr[H_NVEH] = 0;
   }
@@ -786,7 +791,9 @@ __device__ __forceinline__ bool run_instance(const DevSim& D, const RunArgs& A, 
   // ---- write the tile back; a deferred instance leaves its HBM state untouched and queues itself for the overflow
   //      pass (same barriers either way: the instances of a CTA run in lock-step) ----
   const bool bail = misc0[M_BAIL] != 0;
-  if (bail && to_list && tid == 0 && real_slot) D.overflow_list[atomicAdd(D.overflow_count, 1)] = env;
+  if (misc0[M_BAIL] == 1 && to_list && tid == 0 && real_slot) D.overflow_list[atomicAdd(D.overflow_count, 1)] = env;
+  if (!bail && D.heavy_count && tid == 0 && real_slot && hdr[H_NVEH] > D.sc.tile_cap - D.heavy_margin)   // heavy for the NEXT launch
+    { const int hw = D.heavy_count[2] ^ 1; D.heavy_list[hw][atomicAdd(D.heavy_count + hw, 1)] = env; }
   {
     const int n1 = hdr[H_NVEH];
     uint32_t* g = D.veh + (size_t)env * kVehWords * sc.vcap;
@@ -808,6 +815,8 @@ __device__ __forceinline__ bool run_instance(const DevSim& D, const RunArgs& A, 
     }
   }
   if (!bail) {
+    if (tid == 0 && D.heavy_count) hdr[H_DONE] = D.heavy_count[3] + 1;
+    __syncwarp();
     if (tid < kHdrInts) D.hdr[(size_t)env * kHdrInts + tid] = hdr[tid];
     for (int i = tid; i < m.n_tls; i += BLOCK) {
       D.tls_phase[(size_t)env * m.n_tls + i] = T.tls_phase[i];
@@ -820,7 +829,7 @@ __device__ __forceinline__ bool run_instance(const DevSim& D, const RunArgs& A, 
     }
   }
   PCLK(PC_WRITE);
-  return bail;
+  return misc0[M_BAIL] == 1;
 }
 
 // Persistent launch: the grid holds as many CTAs as are resident at once (148 SMs x CTAs/SM); each CTA
@@ -843,6 +852,34 @@ __global__ void __launch_bounds__(TPI * G, MINB) k_run(const __grid_constant__ D
     if (threadIdx.x % TPI == 0) mbar_init((uint64_t*)(my + m.off_mbar), 1);
     __syncthreads();
   }
+  const bool has_next = D.overflow_count != nullptr && !D.from_list;      // somebody can take what outgrows this tile
+  const bool redo = G > 1 && D.sc.redo_cap > 0;
+  const bool tma = D.use_tma && !m.gmem;
+  if constexpr (G > 1) {
+    // ---- the heavy instances of the previous launch first: each by the whole CTA on the redo tile ----
+    if (redo && D.heavy_count && D.heavy_count[D.heavy_count[2]] > 0) {
+      const int hc = D.heavy_count[2];
+      const int nh = D.heavy_count[hc];
+      const SmemLayout mb = make_layout_ex(D.sc, D.sc.redo_cap, D.sc.redo_single, 0);
+      bool any = false;
+      uint32_t unused_parity = 0;
+      for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_env = atomicAdd(D.heavy_taken, 1);
+        __syncthreads();
+        const int idx = s_env;
+        if (idx >= nh) break;
+        if (!any && tma) { if (threadIdx.x % TPI == 0) mbar_inval((uint64_t*)(my + m.off_mbar)); __syncthreads(); }
+        any = true;
+        run_instance<TPI * G, 1>(D, A, mb, smem, smem, D.heavy_list[hc][idx], true, unused_parity, has_next, has_next, false, false);
+      }
+      if (any && tma) {
+        __syncthreads();
+        if (threadIdx.x % TPI == 0) mbar_init((uint64_t*)(my + m.off_mbar), 1);
+      }
+      __syncthreads();
+    }
+  }
 #pragma unroll 1
   for (;;) {
     if (D.persistent) {
@@ -857,10 +894,8 @@ __global__ void __launch_bounds__(TPI * G, MINB) k_run(const __grid_constant__ D
     const int slot = env0 + (int)(threadIdx.x / TPI);
     const int item = min(slot, n_work - 1);
     const int env = D.from_list ? D.overflow_list[item] : item;
-    const bool has_next = D.overflow_count != nullptr && !D.from_list;      // somebody can take what outgrows this tile
-    const bool redo = G > 1 && D.sc.redo_cap > 0;
-    const bool tma = D.use_tma && !m.gmem;
-    const bool bail = run_instance<TPI, G>(D, A, m, my, vb, env, slot < n_work, tma_parity, has_next || redo, has_next && !redo, tma);
+    const bool bail = run_instance<TPI, G>(D, A, m, my, vb, env, slot < n_work, tma_parity, has_next || redo, has_next && !redo, tma,
+                                           redo && D.heavy_count != nullptr);
     if constexpr (G > 1) {
       if (redo) {   // instances of this group that outgrew their slot: the whole CTA steps them again, one at a time
         __shared__ int s_redo[G];
@@ -878,7 +913,7 @@ __global__ void __launch_bounds__(TPI * G, MINB) k_run(const __grid_constant__ D
           const SmemLayout mb = make_layout_ex(D.sc, D.sc.redo_cap, D.sc.redo_single, 0);
           uint32_t unused_parity = 0;
           for (int r = 0; r < nr; ++r) {
-            run_instance<TPI * G, 1>(D, A, mb, smem, smem, s_redo[r], true, unused_parity, has_next, has_next, false);
+            run_instance<TPI * G, 1>(D, A, mb, smem, smem, s_redo[r], true, unused_parity, has_next, has_next, false, false);
             __syncthreads();
           }
           if (tma) {
@@ -964,6 +999,14 @@ __global__ void k_stats(DevSim D, RsStats* out) {
   out[env] = st;
 }
 
+// after every env-step launch: the list the launch filled becomes the one the next launch reads
+__global__ void k_heavy_flip(int32_t* heavy_count) {
+  const int cur = heavy_count[2] ^ 1;
+  heavy_count[2] = cur;
+  heavy_count[cur ^ 1] = 0;
+  heavy_count[3] += 1;
+}
+
 // Batched WaveAgent.act (agents/maxwave.py:18-38): first maximum, in the reference's evaluation order
 // (the iteration order of valid_acts[signal]), of obs[p0] + obs[p1] over the valid phase pairs.
 // obs = states.mplight[1:] (MAXPRESSURE, agents/maxpressure.py:13-18) or states.wave (MAXWAVE).
@@ -1005,7 +1048,8 @@ struct RsSim {
   int resident_ctas;
   // overflow pass (see rs_create): same kernel, whole store in the global workspace, instances from overflow_list
   bool two_pass; SmemLayout layout2; int block2, group2, minb2, resident_ctas2; unsigned char* workspace2;
-  int32_t* counters;   // [0] work counter of the fast pass, [1] of the overflow pass, [2] instances deferred to it, [3] redone in-CTA
+  int32_t* counters;   // [0] work counter of the fast pass, [1] of the overflow pass, [2] instances deferred to it, [3] redone
+                       // in-CTA, [4] work counter over the heavy list; zeroed before every launch
   std::vector<void*> allocs;
   int64_t launches;
   cudaEvent_t ev0, ev1, ev_done;
@@ -1089,10 +1133,11 @@ static DevSim overflow_view(const RsSim* s) {
 }
 
 static int run(RsSim* s, const RunArgs& a, cudaStream_t st) {
-  if (s->d.persistent) CK(cudaMemsetAsync(s->counters, 0, 4 * sizeof(int32_t), st));
+  if (s->d.persistent) CK(cudaMemsetAsync(s->counters, 0, 8 * sizeof(int32_t), st));
   TRY(launch_variant(s, s->block, s->group, s->minb, s->d, s->layout.total, s->resident_ctas, s->d.n_env, a, st));
   if (s->two_pass)
     TRY(launch_variant(s, s->block2, s->group2, s->minb2, overflow_view(s), s->layout2.total, s->resident_ctas2, s->d.n_env, a, st));
+  if (s->d.heavy_count) { k_heavy_flip<<<1, 1, 0, st>>>(s->d.heavy_count); s->launches += 1; CK(cudaGetLastError()); }
   return 0;
 }
 
@@ -1367,7 +1412,7 @@ extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, ui
   const char* et = getenv("RESCO_B200_TMA");
   s->d.use_tma = et ? atoi(et) : 1;
   s->n_sm = prop.multiProcessorCount;
-  TRY(dev_alloc(s, s->counters, 4));
+  TRY(dev_alloc(s, s->counters, 8));
   s->d.work_counter = s->counters;
   s->d.redo_count = s->counters + 3;
   TRY(dev_alloc(s, s->d.phase_clocks, 24));
@@ -1392,6 +1437,13 @@ extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, ui
     if (cap > tile) { s->d.sc.redo_cap = cap; s->d.sc.redo_single = single1; }
   }
   s->two_pass = !gmem && (s->d.sc.redo_cap > 0 ? s->d.sc.redo_cap : tile) < store;
+  s->d.heavy_count = nullptr; s->d.heavy_list[0] = s->d.heavy_list[1] = nullptr; s->d.heavy_taken = s->counters + 4;
+  s->d.heavy_margin = 16;
+  if (s->d.sc.redo_cap > 0 && !(getenv("RESCO_B200_HEAVY") && atoi(getenv("RESCO_B200_HEAVY")) == 0)) {
+    s->d.persistent = 1;
+    TRY(dev_alloc(s, s->d.heavy_list[0], N)); TRY(dev_alloc(s, s->d.heavy_list[1], N));
+    TRY(dev_alloc(s, s->d.heavy_count, 4));
+  }
   s->block2 = 512; s->group2 = 1; s->minb2 = 1;
   if (s->two_pass) {
     s->d.persistent = 1;
@@ -1443,6 +1495,7 @@ extern "C" int rs_reset(RsSim* s, uint64_t seed, int64_t first_env_id, void* str
   s->d.seed = seed; s->d.first_env_id = first_env_id;
   s->graph_policy = 0;   // the captured kernels carry the old seed
   k_reset<<<s->d.n_env, 64, 0, (cudaStream_t)stream>>>(s->d);
+  if (s->d.heavy_count) CK(cudaMemsetAsync(s->d.heavy_count, 0, 4 * sizeof(int32_t), (cudaStream_t)stream));   // empty network: nobody is heavy
   s->launches += 1;
   CK(cudaGetLastError());
   return 0;

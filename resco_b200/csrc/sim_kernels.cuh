@@ -39,7 +39,9 @@ constexpr int kHdrInts = 16;
 constexpr uint32_t kArrived = 0xFFFFu;
 
 // header slots (ints; floats bit-cast)
-enum { H_TICK = 0, H_NVEH, H_EPOCH, H_NINS, H_NARR, H_ANOM, H_ACTIVE, H_F_DELAY_ARR, H_F_DUR_ARR, H_F_PENDING, H_NREF, H_F_WAIT_ARR };
+// H_DONE: launch stamp (launch epoch + 1) of the last launch that stepped the instance; it sits in the same 32-byte
+// sector as H_NVEH, so a CTA staging the header sees both from the same write-back
+enum { H_TICK = 0, H_NVEH, H_EPOCH, H_NINS, H_NARR, H_ANOM, H_ACTIVE, H_DONE, H_F_DELAY_ARR, H_F_DUR_ARR, H_F_PENDING, H_NREF, H_F_WAIT_ARR };
 
 // vtype table columns
 enum { VT_LEN = 0, VT_GAP, VT_ACCEL, VT_DECEL, VT_TAU, VT_SIGMA, VT_VMAX, VT_DEV };
@@ -115,6 +117,14 @@ struct DevSim {
   int32_t* overflow_count;    // instances the fast pass deferred (tile outgrown); null: this launch does not defer
   int32_t* overflow_list;     // [N] their local ids
   int32_t* redo_count;        // instances stepped again inside their CTA (redo_cap) during this launch
+  // Heavy list (launches with an in-CTA redo tile): instances that END a launch with more than tile_cap - heavy_margin
+  // vehicles are listed for the next launch, which steps them FIRST, each by a whole CTA on the redo tile, while the
+  // other CTAs start on the groups -- the long items lead, the short ones fill in (no tail behind a late redo).
+  int32_t* heavy_list[2];     // [N] each; [heavy_cur] is read by this launch, the other one is filled by it
+  int32_t* heavy_count;       // [4]: [0], [1] entries of the two lists, [2] = heavy_cur, the list THIS launch reads, [3] launch
+                              // epoch (device side so that a replayed CUDA graph sees them; k_heavy_flip after every launch)
+  int32_t* heavy_taken;       // work counter over heavy_list[heavy_cur]
+  int32_t heavy_margin;
   int32_t from_list;          // this launch IS the overflow pass: instance ids come from overflow_list[0 .. *overflow_count)
   unsigned long long* phase_clocks;   // [24] diagnostics (RS_PHASE_CLOCKS builds)
   int32_t persistent;

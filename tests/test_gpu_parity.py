@@ -332,7 +332,7 @@ def test_batched_states_from_the_kernel_match_dict_view(map_name, key, rkey):
 
 @pytest.mark.parametrize("map_name,tile,mode,policy", [("cologne8", 0, "gmem", "cyclic"), ("cologne8", 32, "redo", "maxpressure"),
                                                        ("cologne8", 32, "list", "maxpressure"), ("ingolstadt21", 256, "list", "cyclic"),
-                                                       ("grid4x4", 64, "redo+list", "cyclic")])
+                                                       ("grid4x4", 64, "redo+list", "maxpressure")])
 def test_store_larger_than_the_tile(map_name, tile, mode, policy, monkeypatch):
     """The vehicle store is not bounded by one CTA's shared memory, and results do not depend on the tile size.
     gmem: RESCO_B200_GMEM=1, the whole store lives in the per-CTA global-memory workspace (tile_buffers == 0).
@@ -340,7 +340,8 @@ def test_store_larger_than_the_tile(map_name, tile, mode, policy, monkeypatch):
           again at once by its whole CTA on a tile laid over the CTA's shared memory.
     list: the same with the in-CTA redo switched off (RESCO_B200_REDO=0), and ingolstadt21 with a 256-vehicle tile (one
           instance per CTA): instances go on the overflow list and through the overflow pass (global workspace).
-    redo+list: grid4x4 with a 64-vehicle tile under a jamming policy: the in-CTA redo tile is outgrown too.
+    redo+list: grid4x4 with a 64-vehicle tile and synthetic demand above capacity (~2600 vehicles per instance): the
+          in-CTA redo tile is outgrown too.
     Always the same kernel and bit-identical results, nothing refused."""
     if mode == "gmem":
         monkeypatch.setenv("RESCO_B200_GMEM", "1")
@@ -348,8 +349,9 @@ def test_store_larger_than_the_tile(map_name, tile, mode, policy, monkeypatch):
         monkeypatch.setenv("RESCO_B200_REDO", "0")
     n_env = 11
     kw = dict(tile_vcap=tile)
-    if mode == "redo+list":
-        kw["vcap"] = 4096
+    if mode == "redo+list":      # synthetic demand far above capacity: about 2600 vehicles per instance
+        from resco_b200.scenario.synth import synth_demand
+        kw.update(vcap=4096, synthetic=synth_demand(util.load(map_name), 900))
     sc, m, g, o = _pair(map_name, n_env, **kw)
     info = g.tile_info()
     if mode == "gmem":
@@ -359,10 +361,8 @@ def test_store_larger_than_the_tile(map_name, tile, mode, policy, monkeypatch):
         assert (info["redo_vcap"] > tile) == ("redo" in mode) and info["overflow_pass"] == ("list" in mode), info
     g.observe(); o.observe()
     redone = deferred = 0
-    steps = 90 if mode == "redo+list" else 60
-    for step in range(steps):
-        act = util.cyclic_actions(m, n_env, step, period=9 if mode == "redo+list" else 3) if policy == "cyclic" \
-            else util.maxpressure_actions(sc, m, o.obs()["mplight"])
+    for step in range(60):
+        act = util.cyclic_actions(m, n_env, step) if policy == "cyclic" else util.maxpressure_actions(sc, m, o.obs()["mplight"])
         g.env_step(act); o.env_step(act)
         util.assert_same_obs(g.obs(), o.obs(), f"{map_name} step {step}")
         ti = g.tile_info()
