@@ -337,6 +337,8 @@ def run_ours(args):
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         kern_ms, deferred, redone = [], 0, 0
         barrier()
+        if args.profile:
+            torch.cuda.profiler.start()         # ncu --profile-from-start off: captures start at the timed steps
         wall0 = time.perf_counter()
         for i in range(args.steps):
             ensure_room()
@@ -357,6 +359,8 @@ def run_ours(args):
                 ti = sims[0].tile_info()
                 deferred, redone = max(deferred, ti["last_deferred"]), max(redone, ti["last_redone"])
         barrier()
+        if args.profile:
+            torch.cuda.profiler.stop()
         wall = time.perf_counter() - wall0
         dev_ms = sum(a.elapsed_time(b) for a, b in ev)
         st1 = [s.stats() for s in sims]
@@ -573,6 +577,7 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--preroll", type=int, default=-1, help="untimed env steps after reset before warm-up (-1: the config's)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="cudaProfilerStart/Stop around the timed steps (ncu --profile-from-start off)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -305,8 +305,8 @@ int rs_get_launch_shape(RsSim* sim, int32_t* threads_per_instance, int32_t* inst
 /* the vehicle store and the tile (diagnostics / bench `config`): vehicles per instance in the fast pass's tile, in the
  * HBM store, and in the tile a CTA lays over its whole shared memory to step an instance that outgrew its slot again
  * (0: none, one instance per CTA); whether an overflow pass out of the global-memory workspace exists for what outgrows
- * those; how many instances the LAST launch stepped again in-CTA / deferred to the overflow pass (these two synchronise
- * the device).  Any pointer may be NULL. */
+ * those; how many instances the LAST launch stepped with a whole CTA on that tile (from the heavy list, or again after
+ * outgrowing their slot) / deferred to the overflow pass (these two synchronise the device).  Any pointer may be NULL. */
 int rs_get_tile_info(RsSim* sim, int32_t* tile_vcap, int32_t* store_vcap, int32_t* redo_vcap, int32_t* has_overflow_pass,
                      int32_t* last_redone, int32_t* last_deferred);
 /* device time (ms) of the last rs_env_step's kernels, CUDA events on the launching stream */

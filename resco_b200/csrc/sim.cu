@@ -373,7 +373,7 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
   {
     const int n_after = misc[M_NAFTER], n_ok = misc[M_NOK];
     const bool all = n_after + n_ok <= m.vcap;
-    if (!all && misc[M_MAYDEFER] && tid == 0) misc[M_BAIL] = 1;   // tile outgrown (not the store): defer, do not refuse
+    if (!all && misc[M_MAYDEFER] && tid == 0 && misc[M_BAIL] == 0) misc[M_BAIL] = 1;   // (a slot skipped for the heavy list stays skipped)   // tile outgrown (not the store): defer, do not refuse
     for (int j = tid; j < nokc; j += BLOCK) {
       const int o = oklist[j];
       if (cand[o].ok_dd < 0) continue;
@@ -532,6 +532,9 @@ __device__ __forceinline__ void observe_body(const DevSim& D, const SmemLayout& 
   const DevScenario& sc = D.sc;
   const int tid = threadIdx.x % BLOCK, lane_id = tid & 31, wid = tid >> 5, nw = BLOCK / 32;
   int32_t* hdr = (int32_t*)(smem + m.off_hdr);
+  // an instance that is not stepped by this run (deferred, or taken by the heavy list) must not publish anything: the
+  // run that does step it writes its observations, possibly BEFORE this one gets here
+  const bool pub = ((const int32_t*)(smem + m.off_misc))[M_BAIL] == 0;
   float* ob = (float*)(m.off_obs == ~(size_t)0 ? vb + m.off_vn : smem + m.off_obs);   // [5][SL]
   const int SL = m.SL, S = m.S;
   const int e = hdr[H_EPOCH];
@@ -569,7 +572,8 @@ __device__ __forceinline__ void observe_body(const DevSim& D, const SmemLayout& 
       arrv += __shfl_xor_sync(0xffffffffu, arrv, o);
       mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o));
     }
-    if (lane_id == 0) {
+    if (lane_id == 0 && !pub) { ob[0 * SL + q] = queue; ob[1 * SL + q] = appr; ob[2 * SL + q] = tw; ob[3 * SL + q] = mw; ob[4 * SL + q] = ss; }
+    if (lane_id == 0 && pub) {
       ob[0 * SL + q] = queue; ob[1 * SL + q] = appr; ob[2 * SL + q] = tw; ob[3 * SL + q] = mw; ob[4 * SL + q] = ss;
       size_t g = (size_t)env * SL + q;
       D.lane_queue[g] = queue; D.lane_approach[g] = appr; D.lane_total_wait[g] = tw;
@@ -578,7 +582,7 @@ __device__ __forceinline__ void observe_body(const DevSim& D, const SmemLayout& 
   }
   __syncthreads();
   if (tid == 0) hdr[H_EPOCH] = e + 1;
-  for (int x = tid; x < S * 12; x += BLOCK) {
+  for (int x = tid; x < S * 12 && pub; x += BLOCK) {
     int sg = x / 12, mv = x % 12;
     int q0 = __ldg(sc.sig_lane_off + sg);
     float qsum = 0, wsum = 0;
@@ -602,7 +606,7 @@ __device__ __forceinline__ void observe_body(const DevSim& D, const SmemLayout& 
     }
   }
   if (D.out_mask & (RS_OUT_DRQ | RS_OUT_DRQ_NORM)) {   // states.drq / drq_norm (states.py:6-59): the one-hot compares the LANE index with the phase
-    for (int q = tid; q < SL; q += BLOCK) {
+    for (int q = tid; q < SL && pub; q += BLOCK) {
       const int s2 = __ldg(&sc.lane_rec[__ldg(sc.sig_lane + q)].sig);   // rs_create rejects a lane listed by two signals
       const float oh = (q - __ldg(sc.sig_lane_off + s2)) == T.tls_phase[__ldg(sc.sig_tls + s2)] ? 1.0f : 0.0f;
       const float queue = ob[q], appr = ob[SL + q], tw = ob[2 * SL + q], ss = ob[4 * SL + q];
@@ -614,7 +618,7 @@ __device__ __forceinline__ void observe_body(const DevSim& D, const SmemLayout& 
       }
     }
   }
-  for (int sg = tid; sg < S; sg += BLOCK) {
+  for (int sg = tid; sg < S && pub; sg += BLOCK) {
     int q0 = __ldg(sc.sig_lane_off + sg), q1 = __ldg(sc.sig_lane_off + sg + 1);
     int ph = T.tls_phase[__ldg(sc.sig_tls + sg)];
     float tw = 0, ql = 0, mq = 0;
@@ -702,7 +706,7 @@ __device__ __forceinline__ bool run_instance(const DevSim& D, const RunArgs& A, 
     // skip_heavy (2): the instance is on this launch's heavy list -- it was above the heavy threshold when the previous
     // launch wrote it back -- and the CTA that took it there either has stepped it already (launch stamp) or still is
     const int stamp = D.heavy_count ? D.heavy_count[3] + 1 : 0;
-    const int big = (skip_heavy && (hdr[H_DONE] == stamp || hdr[H_NVEH] > m.vcap - D.heavy_margin)) ? 2
+    const int big = (skip_heavy && (hdr[H_DONE] == stamp || hdr[H_NVEH] > D.heavy_thr)) ? 2
                   : ((may_defer && hdr[H_NVEH] > m.vcap) ? 1 : 0);
     misc0[M_BAIL] = big; misc0[M_MAYDEFER] = may_defer ? 1 : 0;
     if (big) hdr[H_NVEH] = 0;
@@ -792,7 +796,7 @@ __device__ __forceinline__ bool run_instance(const DevSim& D, const RunArgs& A, 
   //      pass (same barriers either way: the instances of a CTA run in lock-step) ----
   const bool bail = misc0[M_BAIL] != 0;
   if (misc0[M_BAIL] == 1 && to_list && tid == 0 && real_slot) D.overflow_list[atomicAdd(D.overflow_count, 1)] = env;
-  if (!bail && D.heavy_count && tid == 0 && real_slot && hdr[H_NVEH] > D.sc.tile_cap - D.heavy_margin)   // heavy for the NEXT launch
+  if (!bail && D.heavy_count && tid == 0 && real_slot && hdr[H_NVEH] > D.heavy_thr)   // heavy for the NEXT launch
     { const int hw = D.heavy_count[2] ^ 1; D.heavy_list[hw][atomicAdd(D.heavy_count + hw, 1)] = env; }
   {
     const int n1 = hdr[H_NVEH];
@@ -871,6 +875,7 @@ __global__ void __launch_bounds__(TPI * G, MINB) k_run(const __grid_constant__ D
         if (idx >= nh) break;
         if (!any && tma) { if (threadIdx.x % TPI == 0) mbar_inval((uint64_t*)(my + m.off_mbar)); __syncthreads(); }
         any = true;
+        if (threadIdx.x == 0 && D.redo_count) atomicAdd(D.redo_count, 1);
         run_instance<TPI * G, 1>(D, A, mb, smem, smem, D.heavy_list[hc][idx], true, unused_parity, has_next, has_next, false, false);
       }
       if (any && tma) {
@@ -1111,7 +1116,8 @@ static int launch_run(RsSim* s, const DevSim& d, size_t smem_per_instance, int r
 //  1024/(TPI*G) = 64 registers per thread)
 //  The shapes rs_create can choose (fit_group: 8, 7, 6, 5 instances of 64 threads, 4 of 128, 2 or 1 of 512); other
 //  combinations were measured in round 1 and are no longer compiled.
-#define RS_VARIANTS(X) X(64, 5, 1) X(64, 6, 1) X(64, 7, 1) X(64, 8, 1) X(128, 4, 1) X(512, 1, 1) X(512, 2, 1) X(512, 1, 2)
+#define RS_VARIANTS(X) X(64, 5, 1) X(64, 6, 1) X(64, 7, 1) X(64, 8, 1) X(128, 4, 1) X(512, 1, 1) X(512, 2, 1) X(512, 1, 2) \
+  X(64, 4, 2) X(64, 2, 4) /* experiments: several lock-step groups per SM (RESCO_B200_BLOCK / GROUP / MINB) */
 
 static int launch_variant(RsSim* s, int block, int group, int minb, const DevSim& d, size_t smem_per_instance, int resident,
                           int n_work, const RunArgs& a, cudaStream_t st) {
@@ -1403,6 +1409,7 @@ extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, ui
   // grid4x4 2 x 256 -> 363 k, 2 x 512 -> 377 k; cologne8 8 x 64 -> 3.55 M, 8 x 128 -> 2.53 M)
   s->block = eb ? atoi(eb) : (gmem ? 512 : (s->group >= 5 ? 64 : (s->group == 4 ? 128 : 512)));
   if (er) s->minb = atoi(er) != 0 ? 1024 / (s->block * s->group) : 1;
+  if (getenv("RESCO_B200_MINB")) s->minb = atoi(getenv("RESCO_B200_MINB"));
   if (s->d.sc.tile_single && (s->block < 512 || tile > 2 * s->block)) {
     rs_destroy(s);
     return fail(RS_ERR_INVALID, "rs_create: the single-buffer tile needs tile_vcap <= 2 x threads per instance");
@@ -1438,7 +1445,7 @@ extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, ui
   }
   s->two_pass = !gmem && (s->d.sc.redo_cap > 0 ? s->d.sc.redo_cap : tile) < store;
   s->d.heavy_count = nullptr; s->d.heavy_list[0] = s->d.heavy_list[1] = nullptr; s->d.heavy_taken = s->counters + 4;
-  s->d.heavy_margin = 16;
+  s->d.heavy_thr = tile - 16;
   if (s->d.sc.redo_cap > 0 && !(getenv("RESCO_B200_HEAVY") && atoi(getenv("RESCO_B200_HEAVY")) == 0)) {
     s->d.persistent = 1;
     TRY(dev_alloc(s, s->d.heavy_list[0], N)); TRY(dev_alloc(s, s->d.heavy_list[1], N));

@@ -124,7 +124,7 @@ struct DevSim {
   int32_t* heavy_count;       // [4]: [0], [1] entries of the two lists, [2] = heavy_cur, the list THIS launch reads, [3] launch
                               // epoch (device side so that a replayed CUDA graph sees them; k_heavy_flip after every launch)
   int32_t* heavy_taken;       // work counter over heavy_list[heavy_cur]
-  int32_t heavy_margin;
+  int32_t heavy_thr;          // fast tile - margin: the same threshold in every pass / run of the launch
   int32_t from_list;          // this launch IS the overflow pass: instance ids come from overflow_list[0 .. *overflow_count)
   unsigned long long* phase_clocks;   // [24] diagnostics (RS_PHASE_CLOCKS builds)
   int32_t persistent;
