@@ -2,11 +2,10 @@
 """One episode of a RESCO map on the vectorised backend with the reference's MAXPRESSURE / MAXWAVE rule.
 
     python examples/run_episode.py --map cologne8 --n-env 4096                  # B200: N lock-step instances
-    python examples/run_episode.py --map cologne3 --n-env 4 --backend oracle    # CPU oracle (development only)
 
 Prints the per-instance average delay (utils/readXML.py definition) and the env-step throughput.  The agent is the
-library's batched front end: on the device for the CUDA backend (`VecSim.policy_maxpressure`), `HostWaveAgent`-style
-numpy for the oracle."""
+library's batched front end on the device (`VecSim.policy_maxpressure`).  There is no CPU backend: without the CUDA
+library or a Blackwell GPU the constructor raises (episodes on the CPU oracle, for development: tools/anchors.py)."""
 import argparse
 import os
 import sys
@@ -27,34 +26,18 @@ def main():
     ap.add_argument("--map", default="cologne8")
     ap.add_argument("--n-env", type=int, default=1024)
     ap.add_argument("--agent", default="MAXPRESSURE", choices=["MAXPRESSURE", "MAXWAVE"])
-    ap.add_argument("--backend", default="cuda", choices=["cuda", "oracle"])
     ap.add_argument("--seed", type=int, default=1)
     a = ap.parse_args()
     use_wave = a.agent == "MAXWAVE"
     state_fn = states.wave if use_wave else states.mplight
-    backend = None
-    if a.backend == "oracle":
-        sys.path.insert(0, os.path.join(ROOT, "oracle"))
-        from pyoracle import OracleSim
-        backend = lambda m: OracleSim(m, a.n_env, seed=0)                      # noqa: E731
     from resco_b200.multi_signal import load_scenario
     mc = load_scenario(a.map).meta["map_config"]
     env = MultiSignal("example", a.map, None, state_fn, rewards.pressure, end_time=mc["end_time"], step_length=mc["step_length"],
                       yellow_length=mc["yellow_length"], max_distance=50 if use_wave else 200, log_dir=None,
-                      n_env=max(a.n_env, 2), seed=a.seed, backend=backend)
+                      n_env=max(a.n_env, 2), seed=a.seed)
     sc = env.scenario
     pairs, va, sig = sc.meta["phase_pairs"], sc.meta["valid_acts"], env.signal_ids
-    if a.backend == "cuda":
-        act = lambda obs: env.sim.policy_maxpressure(pairs, va, sig, use_wave=use_wave)     # noqa: E731
-    else:
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        import util
-
-        def act(obs):
-            x = obs.numpy()
-            if use_wave:
-                x = np.concatenate([np.zeros_like(x[:, :, :1]), x], 2)
-            return util.maxpressure_actions(sc, env.marshalled, x)
+    act = lambda obs: env.sim.policy_maxpressure(pairs, va, sig, use_wave=use_wave)     # noqa: E731
     obs = env.reset()
     steps, done, t0 = 0, False, time.perf_counter()
     while not done:

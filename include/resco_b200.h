@@ -206,6 +206,11 @@ int rs_destroy(RsSim* sim);
 /* MultiSignal.reset(): fresh episode state for every instance (per-instance RNG key = seed + global id).
  * `first_env_id` is the global id of local instance 0 (multi-GPU sharding keeps results invariant). */
 int rs_reset(RsSim* sim, uint64_t seed, int64_t first_env_id, void* stream);
+/* The demand of the next episode: per origin lane, the range [h_origin_off[o], h_origin_off[o + 1]) of the trip table
+ * (trip_depart / trip_route / trip_vtype, departure order within the range) that may depart -- the route file of the run
+ * (`route + '_' + str(self.run) + '.rou.xml'`, multi_signal.py:124) when the trip table holds several files back to
+ * back.  Call before rs_reset; all instances share the window.  [n_origins + 1] host ints, ranges inside the table. */
+int rs_set_demand_window(RsSim* sim, const int32_t* h_origin_off);
 /* trafficlight.setPhase(id, idx) for all instances: phase[N,S] device ptr, mask[N,S] (may be NULL) */
 int rs_set_phase(RsSim* sim, const int32_t* d_phase, const uint8_t* d_mask, void* stream);
 /* simulationStep() x n_ticks */

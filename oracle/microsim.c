@@ -948,6 +948,13 @@ void orc_reset(OrcSim* s, uint64_t seed, int64_t first_env_id) {
   }
 }
 
+/* per-origin range of the trip table that is the next episode's demand (rs_set_demand_window) */
+int orc_set_demand_window(OrcSim* s, const int32_t* origin_off) {
+  if (s->sc.synthetic) return -1;
+  memcpy((int32_t*)s->sc.origin_off, origin_off, sizeof(int32_t) * (size_t)(s->sc.n_origins + 1));
+  return 0;
+}
+
 void orc_set_phase(OrcSim* s, const int32_t* phase, const uint8_t* mask) {
   int S = s->sc.n_signals;
   for (int e = 0; e < s->n_env; ++e)

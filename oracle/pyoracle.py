@@ -37,6 +37,7 @@ def lib():
         _LIB.orc_destroy.argtypes = [C.c_void_p]
         _LIB.orc_reset.argtypes = [C.c_void_p, C.c_uint64, C.c_int64]
         _LIB.orc_set_phase.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _LIB.orc_set_demand_window.argtypes = [C.c_void_p, C.c_void_p]
         _LIB.orc_tick.argtypes = [C.c_void_p, C.c_int32]
         _LIB.orc_observe.argtypes = [C.c_void_p]
         _LIB.orc_env_step.argtypes = [C.c_void_p, C.c_void_p]
@@ -95,6 +96,12 @@ class OracleSim:
 
     def reset(self, seed: int = 0, first_env_id: int = 0):
         lib().orc_reset(self._h, seed, first_env_id)
+
+    def set_demand_window(self, origin_off):
+        w = np.ascontiguousarray(origin_off, np.int32)
+        assert w.shape == (self.m.struct.n_origins + 1,)
+        if lib().orc_set_demand_window(self._h, w.ctypes.data) != 0:
+            raise RuntimeError("set_demand_window: synthetic demand has no trip table")
 
     def set_phase(self, phase, mask=None):
         p = np.ascontiguousarray(phase, np.int32)

@@ -1508,6 +1508,19 @@ extern "C" int rs_reset(RsSim* s, uint64_t seed, int64_t first_env_id, void* str
   return 0;
 }
 
+extern "C" int rs_set_demand_window(RsSim* s, const int32_t* h_origin_off) {
+  if (!s || !h_origin_off) return fail(RS_ERR_INVALID, "rs_set_demand_window: bad arguments");
+  const int O = s->d.sc.n_origins;
+  if (s->d.sc.synthetic) return fail(RS_ERR_INVALID, "rs_set_demand_window: the scenario has synthetic demand, not a trip table");
+  for (int o = 0; o < O; ++o)
+    if (h_origin_off[o] < 0 || h_origin_off[o] > h_origin_off[o + 1] || h_origin_off[o + 1] > s->d.sc.n_trips)
+      return fail(RS_ERR_INVALID, "rs_set_demand_window: range outside the trip table");
+  CK(cudaSetDevice(s->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(const_cast<int32_t*>(s->d.sc.origin_off), h_origin_off, sizeof(int32_t) * (O + 1), cudaMemcpyHostToDevice));
+  return 0;
+}
+
 extern "C" int rs_set_phase(RsSim* s, const int32_t* d_phase, const uint8_t* d_mask, void* stream) {
   if (!s || !d_phase) return fail(RS_ERR_INVALID, "rs_set_phase: bad arguments");
   int total = s->d.n_env * s->d.sc.n_signals;

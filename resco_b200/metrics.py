@@ -48,10 +48,20 @@ def write_tripinfo(path: str, scenario, records: Dict[str, np.ndarray], running:
     return n
 
 
+def episode_trip_range(scenario, episode: int = 0):
+    """(first, last + 1) of the trip table rows that are the demand of `episode` (the route file of that run)."""
+    bank = scenario.arrays.get("bank_origin_off")
+    if bank is None:
+        return 0, len(scenario.arrays["trip_depart"])
+    e = episode % bank.shape[0]
+    return int(bank[e, 0]), int(bank[e, -1])
+
+
 def avg_delay_from_tripinfo(path: str, scenario=None, end_time: Optional[float] = None,
-                            vehicle_demand: bool = False, metric: str = "timeLoss") -> float:
+                            vehicle_demand: bool = False, metric: str = "timeLoss", episode: int = 0) -> float:
     """readXML.py:27-77 for one tripinfo file.  `vehicle_demand`: the route file holds <vehicle> elements
-    (grid4x4 / arterial4x4), so never-departed vehicles are charged; needs `scenario` + `end_time`."""
+    (grid4x4 / arterial4x4), so never-departed vehicles are charged; needs `scenario` + `end_time` (+ `episode`: which
+    of the compiled route files the run used)."""
     root = ET.parse(path).getroot()
     num_trips, total = 0, 0.0
     last_departure_time, last_depart_id = 0.0, ''
@@ -66,8 +76,9 @@ def avg_delay_from_tripinfo(path: str, scenario=None, end_time: Optional[float] 
                 last_depart_id = child.attrib['id']
     if metric == 'timeLoss' and vehicle_demand:
         begin = float(scenario.meta["begin"])
-        ids = scenario.meta["trip_ids"]
-        sched = begin + scenario.arrays["trip_depart"].astype(np.float64)
+        t0, t1 = episode_trip_range(scenario, episode)
+        ids = scenario.meta["trip_ids"][t0:t1]
+        sched = begin + scenario.arrays["trip_depart"][t0:t1].astype(np.float64)
         if last_depart_id not in ids:
             raise ValueError('Wrong trip file')
         last_sched = float(sched[ids.index(last_depart_id)])

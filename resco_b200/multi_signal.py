@@ -143,6 +143,7 @@ class MultiSignal(_EnvBase):
             self.action_space.append(_mk_discrete(len(self.phases[ts])))
         self.n_agents = self.ts_starter
         self.run = 0
+        self.demand_episode = 0
         self.metrics = []
         self.connection_name = (run_name + '-' + map_name + '-' + str(len(lights)) + '-' + state_fn.__name__ + '-'
                                 + reward_fn.__name__)
@@ -296,6 +297,13 @@ class MultiSignal(_EnvBase):
         self.metrics = []
         self.run += 1
         self._episode_seed = (self.run if self.seed is None else int(self.seed) + self.run - 1)
+        # grid4x4 / arterial4x4: a different route file every episode (multi_signal.py:124); the compiled scenario
+        # holds the first `n_demand_episodes` of them, run r uses file ((r - 1) mod n) + 1
+        bank = self.scenario.arrays.get("bank_origin_off")
+        self.demand_episode = 0
+        if bank is not None and hasattr(self.sim, "set_demand_window"):
+            self.demand_episode = (self.run - 1) % bank.shape[0]
+            self.sim.set_demand_window(bank[self.demand_episode])
         self.sim.reset(self._episode_seed, 0)
         self._tick = 0
         self.signal_ids = list(self.all_ts_ids)

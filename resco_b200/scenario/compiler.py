@@ -344,8 +344,18 @@ class Router:
 
 
 def compile_demand(arrays: Dict[str, np.ndarray], meta: Dict[str, object], idx: Dict[str, object],
-                   demand: Demand, begin: float) -> Tuple[Dict[str, np.ndarray], Dict[str, object]]:
-    """vTypes, deduplicated route table (edge + ok-lane mask per step) and the trip table."""
+                   demand, begin: float) -> Tuple[Dict[str, np.ndarray], Dict[str, object]]:
+    """vTypes, deduplicated route table (edge + ok-lane mask per step) and the trip table.
+
+    `demand` is one Demand or a list of them: the reference loads a different route file every episode on grid4x4 and
+    arterial4x4 (``route + '_' + str(self.run) + '.rou.xml'``, multi_signal.py:124).  A list compiles into ONE trip
+    table -- the episodes back to back, each grouped by origin lane -- over a shared route / origin / vType table, plus
+    ``bank_origin_off[R, O + 1]``: per episode, the range of the trip table that belongs to each origin lane.
+    ``origin_off`` is the first episode's row; MultiSignal.reset() installs the row of its run (rs_set_demand_window)."""
+    demands = list(demand) if isinstance(demand, (list, tuple)) else [demand]
+    demand = Demand({k: v for d in demands for k, v in d.vtypes.items()}, [t for d in demands for t in d.trips])
+    episode_of: List[int] = [e for e, d in enumerate(demands) for _ in d.trips]
+    file_index: List[int] = [i for d in demands for i in range(len(d.trips))]
     edge_idx: Dict[str, int] = idx["edge_idx"]
     a = arrays
     E = len(meta["edge_ids"])
@@ -468,16 +478,22 @@ def compile_demand(arrays: Dict[str, np.ndarray], meta: Dict[str, object], idx: 
             continue
         lane_i = (m0 & -m0).bit_length() - 1      # lowest-index usable lane ("best"-lane insertion)
         origin_lane = int(a["edge_lane0"][edges[0]]) + lane_i
-        rows.append((origin_lane, tr.depart - begin, fi, rid, vti))
-    rows.sort(key=lambda r: (r[0], r[1], r[2]))
-    T = len(rows)
+        rows.append((origin_lane, tr.depart - begin, file_index[fi], rid, vti, episode_of[fi], fi))
+    rows.sort(key=lambda r: (r[5], r[0], r[1], r[2]))
     origins = sorted({r[0] for r in rows})
     o_index = {o: i for i, o in enumerate(origins)}
     origin_lane = np.array(origins, np.int32)
-    origin_off = np.zeros(len(origins) + 1, np.int32)
+    R, O = len(demands), len(origins)
+    counts = np.zeros((R, O), np.int64)
     for r in rows:
-        origin_off[o_index[r[0]] + 1] += 1
-    origin_off = np.cumsum(origin_off).astype(np.int32)
+        counts[r[5], o_index[r[0]]] += 1
+    bank = np.zeros((R, O + 1), np.int32)
+    base = 0
+    for e in range(R):
+        bank[e, 0] = base
+        bank[e, 1:] = base + np.cumsum(counts[e])
+        base = int(bank[e, O])
+    origin_off = bank[0].copy()
     out = dict(
         vtype=vt, vtype_bit=vt_bit,
         route_off=np.array(route_off, np.int32), route_edge=np.array(route_edges, np.int32).reshape(-1),
@@ -488,9 +504,11 @@ def compile_demand(arrays: Dict[str, np.ndarray], meta: Dict[str, object], idx: 
         trip_route=np.array([r[3] for r in rows], np.int32).reshape(-1),
         trip_vtype=np.array([r[4] for r in rows], np.int32).reshape(-1),
     )
-    dmeta = dict(vtype_ids=vt_ids, n_trips_file=len(demand.trips), n_unroutable=n_unroutable,
-                 n_before_begin=n_before_begin,
-                 trip_ids=[demand.trips[r[2]].id for r in rows])
+    if R > 1:
+        out["bank_origin_off"] = bank
+    dmeta = dict(vtype_ids=vt_ids, n_trips_file=len(demands[0].trips), n_unroutable=n_unroutable,
+                 n_before_begin=n_before_begin, n_demand_episodes=R,
+                 trip_ids=[demand.trips[r[6]].id for r in rows])
     return out, dmeta
 
 

@@ -41,7 +41,7 @@ EXPORTS = ["rs_last_error", "rs_abi_version", "rs_create", "rs_destroy", "rs_res
            "rs_observe", "rs_env_step", "rs_env_step_host", "rs_env_step_host_async", "rs_wait", "rs_policy_maxpressure", "rs_host_agent_wave", "rs_get_obs", "rs_get_stats",
            "rs_dump_vehicles", "rs_get_phases", "rs_get_trip_records", "rs_kernel_launches", "rs_last_step_ms", "rs_get_launch_shape",
            "rs_select_outputs", "rs_set_host_obs", "rs_frap_load", "rs_policy_frap", "rs_policy_random", "rs_env_step_policy",
-           "rs_get_tile_info"]
+           "rs_get_tile_info", "rs_set_demand_window"]
 
 
 def load_library():
@@ -59,6 +59,7 @@ def load_library():
     lib.rs_destroy.argtypes = [C.c_void_p]
     lib.rs_reset.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p]
     lib.rs_set_phase.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.rs_set_demand_window.argtypes = [C.c_void_p, C.c_void_p]
     lib.rs_tick.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
     lib.rs_observe.argtypes = [C.c_void_p, C.c_void_p]
     lib.rs_env_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -192,6 +193,12 @@ class VecSim:
     # simulation --------------------------------------------------------------------------------
     def reset(self, seed: int = 0, first_env_id: int = 0):
         _check(self.lib, self.lib.rs_reset(self._h, seed, first_env_id, self._stream()))
+
+    def set_demand_window(self, origin_off):
+        """Per origin lane, the range of the trip table that may depart in the next episode (call before reset)."""
+        w = np.ascontiguousarray(origin_off, np.int32)
+        assert w.shape == (self.m.struct.n_origins + 1,)
+        _check(self.lib, self.lib.rs_set_demand_window(self._h, w.ctypes.data))
 
     def set_phase(self, phase, mask=None):
         t = self._torch

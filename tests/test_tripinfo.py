@@ -67,8 +67,10 @@ def test_tripinfo_gpu_matches_oracle(tmp_path):
 def test_never_departed_rule(tmp_path):
     """<vehicle>-type demand: vehicles scheduled after the last departed one are charged end_time - depart."""
     sc = util.load("grid4x4")
-    ids = sc.meta["trip_ids"]
-    sched = sc.meta["begin"] + sc.arrays["trip_depart"].astype(float)
+    from resco_b200.metrics import episode_trip_range
+    t0, t1 = episode_trip_range(sc, 0)          # the scenario holds several route files back to back: episode 0
+    ids = sc.meta["trip_ids"][t0:t1]
+    sched = sc.meta["begin"] + sc.arrays["trip_depart"][t0:t1].astype(float)
     order = np.argsort(sched, kind="stable")
     a, b = int(order[0]), int(order[len(order) // 2])
     p = tmp_path / "t.xml"

@@ -16,6 +16,7 @@ from resco_b200.scenario.compiler import compile_scenario  # noqa: E402
 
 REF = os.environ.get('RESCO_REFERENCE', '/root/reference/resco_benchmark')
 OUT = os.path.join(os.path.dirname(__file__), '..', 'resco_b200', 'data')
+EPISODES = int(os.environ.get('RESCO_EPISODES', '10'))
 
 
 def main(maps):
@@ -35,8 +36,10 @@ def main(maps):
             net = read_net(netp)
             # multi_signal.py:33-37,124: route file <route>/<map>_<run>.rou.xml, run = 1 here
             zp = os.path.join(REF, 'environments', m, m + '.zip')
+            # one demand table per episode: the first EPISODES route files (the zip ships 1400; MultiSignal.reset()
+            # cycles through the compiled ones, run r -> file ((r - 1) % EPISODES) + 1)
             with zipfile.ZipFile(zp) as z:
-                demand = read_routes_xml(z.read(m + '_1.rou.xml').decode(), is_text=True)
+                demand = [read_routes_xml(z.read(f'{m}_{r}.rou.xml').decode(), is_text=True) for r in range(1, EPISODES + 1)]
             begin = float(mc['start_time'])
         sc = compile_scenario(net, demand, m, mc, signal_configs[m], begin)
         # hyper-parameters + manager/worker regions of the FMA2C states/rewards (config/mdp_config.py)
