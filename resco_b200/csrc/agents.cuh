@@ -105,7 +105,8 @@ __global__ void __launch_bounds__(kFrapThreads) k_policy_frap(const float* __res
     fs[x] = acc;
   }
   __syncthreads();
-  // ---- C: pair competition: one thread per (row, pair i), the n - 1 opponents two at a time ----
+  // ---- C: pair competition: one thread per (row, pair i), the n - 1 opponents three at a time so that every weight of
+  //      the 20 x 20 layer (one 128-bit shared-memory broadcast load per four) feeds three FMAs ----
   const int r = tid / n_pairs, i = tid % n_pairs;
   if (r < R) {
     const float* first = fs + (r * n_pairs + i) * 40;
@@ -113,28 +114,41 @@ __global__ void __launch_bounds__(kFrapThreads) k_policy_frap(const float* __res
 #pragma unroll
     for (int k = 0; k < 20; ++k) f[k] = first[k];
     float q = 0.0f;
-    for (int jj = 0; jj < n_pairs - 1; jj += 2) {
-      const bool two = jj + 1 < n_pairs - 1;
-      const int j0 = jj < i ? jj : jj + 1, j1 = two ? (jj + 1 < i ? jj + 1 : jj + 2) : j0;
-      const float* s0 = fs + (r * n_pairs + j0) * 40 + 20;
-      const float* s1 = fs + (r * n_pairs + j1) * 40 + 20;
-      const float* r0 = F.rel[__ldg(comp + i * (n_pairs - 1) + jj)];
-      const float* r1 = F.rel[__ldg(comp + i * (n_pairs - 1) + (two ? jj + 1 : jj))];
-      float c0[20], c1[20];
+    const int n_opp = n_pairs - 1;
+    for (int jj = 0; jj < n_opp; jj += 3) {
+      float c[3][20];
+      bool live[3];
 #pragma unroll
-      for (int k = 0; k < 20; ++k) { c0[k] = fmaxf(f[k] + s0[k], 0.0f) * r0[k]; c1[k] = fmaxf(f[k] + s1[k], 0.0f) * r1[k]; }
-      float o0 = F.w[FP_BMB], o1 = F.w[FP_BMB];
-#pragma unroll 4
-      for (int k2 = 0; k2 < 20; ++k2) {
-        const float* w = F.w + FP_HLW + k2 * 20;
-        float h0 = F.w[FP_HLB + k2], h1 = h0;
+      for (int t = 0; t < 3; ++t) {
+        live[t] = jj + t < n_opp;
+        const int jo = live[t] ? jj + t : jj;                       // a dead slot repeats a live one, its result is dropped
+        const int j = jo < i ? jo : jo + 1;                         // the jo-th OTHER pair, in the reference's order
+        const float* sj = fs + (r * n_pairs + j) * 40 + 20;
+        const float* rl = F.rel[__ldg(comp + i * n_opp + jo)];
 #pragma unroll
-        for (int k = 0; k < 20; ++k) { const float wk = w[k]; h0 = __fmaf_rn(wk, c0[k], h0); h1 = __fmaf_rn(wk, c1[k], h1); }
-        const float bm = F.w[FP_BMW + k2];
-        o0 = __fmaf_rn(bm, fmaxf(h0, 0.0f), o0); o1 = __fmaf_rn(bm, fmaxf(h1, 0.0f), o1);
+        for (int k = 0; k < 20; ++k) c[t][k] = fmaxf(f[k] + sj[k], 0.0f) * rl[k];
       }
-      q += o0;
-      if (two) q += o1;
+      float o[3] = {F.w[FP_BMB], F.w[FP_BMB], F.w[FP_BMB]};
+#pragma unroll 2
+      for (int k2 = 0; k2 < 20; ++k2) {
+        const float4* w4 = reinterpret_cast<const float4*>(F.w + FP_HLW + k2 * 20);
+        const float hb = F.w[FP_HLB + k2];
+        float h[3] = {hb, hb, hb};
+#pragma unroll
+        for (int kq = 0; kq < 5; ++kq) {
+          const float4 w = w4[kq];
+#pragma unroll
+          for (int t = 0; t < 3; ++t) {
+            h[t] = __fmaf_rn(w.x, c[t][4 * kq + 0], h[t]); h[t] = __fmaf_rn(w.y, c[t][4 * kq + 1], h[t]);
+            h[t] = __fmaf_rn(w.z, c[t][4 * kq + 2], h[t]); h[t] = __fmaf_rn(w.w, c[t][4 * kq + 3], h[t]);
+          }
+        }
+        const float bm = F.w[FP_BMW + k2];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) o[t] = __fmaf_rn(bm, fmaxf(h[t], 0.0f), o[t]);
+      }
+#pragma unroll
+      for (int t = 0; t < 3; ++t) if (live[t]) q += o[t];
     }
     qs[r * n_pairs + i] = q;
     const int row = row0 + r;

@@ -15,11 +15,12 @@ for arg in sys.argv[1:]:
     key, rest = arg.split("=")
     path, n_env = rest.rsplit(":", 1)
     rows = list(csv.reader(open(path)))
-    hdr, vals = rows[0], rows[2]
+    hdr, units, vals = rows[0], rows[1], rows[2]
     ci = {n: i for i, n in enumerate(hdr)}
+    SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9}
 
-    def num(name):
-        return float(vals[ci[name]].replace(",", ""))
+    def num(name):      # in bytes / ns / plain counts whatever unit ncu chose to print
+        return float(vals[ci[name]].replace(",", "")) * SCALE.get(units[ci[name]], 1.0)
     n = int(n_env)
     out[key] = dict(n_env_per_launch=n, kernel=vals[ci["Kernel Name"]],
                     dram_bytes_per_env_step=(num("dram__bytes_read.sum") + num("dram__bytes_write.sum")) / n,
