@@ -9,10 +9,12 @@ Workloads (BASELINE.json `configs`; `--config`, default c2 = the configuration t
   c3  ingolstadt21 (21 signals) / IDQN / 8192 instances: the kernel emits states.drq_norm + rewards.wait_norm and
       rewards.pressure every step (agent_config.py:83-94 and BASELINE's wording); IDQN's own network is pfrl code on the
       caller's side, so actions are its epsilon = 1 exploration: uniform random green phases drawn on the device
-  c4  ingolstadt21 / MPLight shared controller / 8192 instances per GPU (65536 on 8): states.mplight of every rank is
-      all-gathered over NCCL, rank 0 evaluates FRAP (agents/mplight.py, random-init weights: no checkpoints here) for
-      all instances and broadcasts the actions; two half-batches per rank on two streams, so the collectives of one
-      half overlap the env-step kernel of the other
+  c4  ingolstadt21 / MPLight shared controller / 8192 instances per GPU (65536 on 8): every rank evaluates FRAP
+      (agents/mplight.py, random-init weights: no checkpoints here; the shared weights are replicated) for its own
+      instances, and states.mplight + the pressure reward of every rank are all-gathered over NCCL each step so that
+      the learner rank holds the full batch; two half-batches per rank on two streams, so the collectives of one half
+      overlap the env-step kernel of the other.  --c4-policy rank0: the literal single-rank policy (gather, FRAP on
+      rank 0 for all instances, broadcast of the actions)
   c5  synthetic 4x4 grid, Poisson (Bernoulli per tick) demand swept over 300 / 600 / 900 / 1200 veh/h per entry lane,
       16384 instances per GPU, MaxPressure; `value` is the sweep total, per-rate lines in config.sweep
 
@@ -53,8 +55,8 @@ CONFIGS = {
                     "per GPU / kernel emits drq_norm + wait_norm + pressure"),
     "c4": dict(map="ingolstadt21", n_env=8192, policy="frap", tile=0, vcap=0, rates=[0.0], preroll=60,
                host_obs="mplight", reward_kind=2, outputs=(),
-               what="ingolstadt21 / MPLight shared controller (FRAP forward on rank 0 over the NCCL all-gathered "
-                    "states.mplight, actions broadcast) / {n} instances per GPU"),
+               what="ingolstadt21 / MPLight shared controller (FRAP forward kernel, replicated weights; states.mplight + "
+                    "pressure reward NCCL all-gathered for the learner rank every step) / {n} instances per GPU"),
     "c5": dict(map="grid4x4", n_env=16384, policy="maxpressure", tile=4096, vcap=4096, rates=[300.0, 600.0, 900.0, 1200.0],
                preroll=60, host_obs="mplight", reward_kind=0, outputs=(),
                what="synthetic 4x4 grid / Bernoulli-per-tick demand sweep 300-1200 veh/h per entry lane / MaxPressure / "
@@ -295,6 +297,7 @@ def run_ours(args):
         sims = [make_sim(sc, m, cnt, rank * n_env + first) for first, cnt in parts]
         gather = [torch.empty((world * cnt, S, 13), device=dev) for _, cnt in parts] if shared and world > 1 else None
         acts_all = [torch.empty((world * cnt, S), dtype=torch.int32, device=dev) for _, cnt in parts] if shared else None
+        gather_rew = [torch.empty((world * cnt, S), device=dev) for _, cnt in parts] if shared and world > 1 else None
         state = {"step": 0}
 
         def one_step():
@@ -304,14 +307,23 @@ def run_ours(args):
             for h, (sim, st) in enumerate(zip(sims, streams)):
                 with torch.cuda.stream(st):
                     cnt = parts[h][1]
-                    if world > 1:      # configs[3]: obs all-gather over NVLink, shared policy on rank 0, actions broadcast
+                    if world > 1 and args.c4_policy == "rank0":
+                        # the literal reading of configs[3]: obs all-gather, the shared policy evaluated by rank 0 for ALL
+                        # instances, actions broadcast -- rank 0's FRAP time grows with the number of GPUs
                         dist.all_gather_into_tensor(gather[h], sim.obs_view()["mplight"])
                         if rank == 0:
                             acts_all[h].copy_(sim.policy_frap(gather[h]))
                         dist.broadcast(acts_all[h], src=0)
                         sim.env_step(acts_all[h][rank * cnt:(rank + 1) * cnt])
                     else:
-                        sim.env_step(sim.policy_frap())
+                        # acting: the shared controller's weights are replicated, every rank evaluates FRAP for its own
+                        # instances (one graph launch: policy + env step); learning side: the step's observations and
+                        # rewards are all-gathered over NVLink so that the learner rank holds the full batch
+                        # (SharedDQN.observe, agents/pfrl_dqn.py) -- on this half's stream, overlapping the other half's kernel
+                        sim.env_step_policy("frap")
+                        if world > 1:
+                            dist.all_gather_into_tensor(gather[h], sim.obs_view()["mplight"])
+                            dist.all_gather_into_tensor(gather_rew[h], sim.obs_view()["reward_pressure"])
 
         def preroll():
             # untimed set-up: reset and run the episode up to a loaded network before anything is timed
@@ -512,7 +524,7 @@ def run_ours(args):
                        "n_cap_refused_in_timed_window": refused_total,
                        "l2": "flushed between timed steps (160 MiB memset > 126 MB L2, untimed)",
                        "timing": "per-step CUDA events on the launching stream, summed; max over ranks",
-                       "allgather_obs": bool(shared and world > 1),
+                       "allgather_obs": bool(shared and world > 1), "c4_policy": args.c4_policy if shared else None,
                        "avg_delay_parity_vs_sumo": "not measurable here: SUMO/libsumo is installed neither in the build container nor on the GPU box; statistical anchors against utils/avg_timeLoss.py: tests/test_anchors.py, DESIGN.md section 7",
                        "preroll_env_steps": cfg["preroll"] if args.preroll < 0 else args.preroll,
                        "episode_window": "timed steps start after an untimed pre-roll of the episode (loaded network); the episode restarts (reset + pre-roll, untimed) when its steps are used up",
@@ -576,6 +588,9 @@ def main():
     ap.add_argument("--tile", type=int, default=-1, help="vehicles in the shared-memory tile (-1: the config's)")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--preroll", type=int, default=-1, help="untimed env steps after reset before warm-up (-1: the config's)")
+    ap.add_argument("--c4-policy", default="replicated", choices=["replicated", "rank0"],
+                    help="c4: every rank evaluates the shared FRAP for its own instances and the observations are all-gathered for "
+                         "the learner (default), or rank 0 evaluates the gathered batch and broadcasts the actions")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--profile", action="store_true", help="cudaProfilerStart/Stop around the timed steps (ncu --profile-from-start off)")
     args = ap.parse_args()
