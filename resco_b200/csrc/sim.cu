@@ -706,7 +706,7 @@ __device__ __forceinline__ bool run_instance(const DevSim& D, const RunArgs& A, 
     // skip_heavy (2): the instance is on this launch's heavy list -- it was above the heavy threshold when the previous
     // launch wrote it back -- and the CTA that took it there either has stepped it already (launch stamp) or still is
     const int stamp = D.heavy_count ? D.heavy_count[3] + 1 : 0;
-    const int big = (skip_heavy && (hdr[H_DONE] == stamp || hdr[H_NVEH] > D.heavy_thr)) ? 2
+    const int big = (!real_slot || (skip_heavy && (hdr[H_DONE] == stamp || hdr[H_NVEH] > D.heavy_thr))) ? 2
                   : ((may_defer && hdr[H_NVEH] > m.vcap) ? 1 : 0);
     misc0[M_BAIL] = big; misc0[M_MAYDEFER] = may_defer ? 1 : 0;
     if (big) hdr[H_NVEH] = 0;
@@ -887,19 +887,21 @@ __global__ void __launch_bounds__(TPI * G, MINB) k_run(const __grid_constant__ D
   }
 #pragma unroll 1
   for (;;) {
+    const int n_work = D.from_list ? *D.overflow_count : D.n_env;
     if (D.persistent) {
       if (threadIdx.x == 0) s_env = atomicAdd(D.work_counter, G);
       __syncthreads();
     }
     PCLK(PC_SCHED);
     const int env0 = D.persistent ? s_env : (int)blockIdx.x * G;
-    const int n_work = D.from_list ? *D.overflow_count : D.n_env;
     if (env0 >= n_work) break;
-    // a slot past the end of the batch repeats the last instance (same inputs -> identical stores)
-    const int slot = env0 + (int)(threadIdx.x / TPI);
+    // an idle slot (past the end of the batch) steps an empty tile and stores nothing
+    const int slot_i = (int)(threadIdx.x / TPI);
+    const int slot = env0 + slot_i;
+    const bool live = slot < n_work;
     const int item = min(slot, n_work - 1);
     const int env = D.from_list ? D.overflow_list[item] : item;
-    const bool bail = run_instance<TPI, G>(D, A, m, my, vb, env, slot < n_work, tma_parity, has_next || redo, has_next && !redo, tma,
+    const bool bail = run_instance<TPI, G>(D, A, m, my, vb, env, live, tma_parity, has_next || redo, has_next && !redo, tma,
                                            redo && D.heavy_count != nullptr);
     if constexpr (G > 1) {
       if (redo) {   // instances of this group that outgrew their slot: the whole CTA steps them again, one at a time
@@ -908,7 +910,7 @@ __global__ void __launch_bounds__(TPI * G, MINB) k_run(const __grid_constant__ D
         __syncthreads();
         if (threadIdx.x == 0) s_nredo = 0;
         __syncthreads();
-        if (bail && slot < n_work && threadIdx.x % TPI == 0) s_redo[atomicAdd(&s_nredo, 1)] = env;
+        if (bail && live && threadIdx.x % TPI == 0) s_redo[atomicAdd(&s_nredo, 1)] = env;
         __syncthreads();
         const int nr = s_nredo;
         if (nr > 0) {   // (s_redo is static shared memory: the redo tile only overwrites the dynamic part)
