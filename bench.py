@@ -46,7 +46,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CONFIGS = {
-    "c2": dict(map="cologne8", n_env=4096, policy="maxpressure", tile=128, vcap=0, rates=[0.0], preroll=90,
+    "c2": dict(map="cologne8", n_env=4096, policy="maxpressure", tile=128, vcap=1024, rates=[0.0], preroll=90,
                host_obs="mplight", reward_kind=0, outputs=(),
                what="cologne8 (8 signals) / MaxPressure / {n} lock-step instances per GPU"),
     "c3": dict(map="ingolstadt21", n_env=8192, policy="random", tile=0, vcap=0, rates=[0.0], preroll=60,
