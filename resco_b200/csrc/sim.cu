@@ -1227,6 +1227,18 @@ extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, ui
       r.tls = sc->link_tls[k]; r.tlidx = sc->link_tlidx[k]; r.state = sc->link_state[k]; r.cont = sc->link_cont[k];
       r.via_len = sc->link_via_len[k]; r.last_int = sc->link_last_int[k]; r.parent = sc->link_parent[k];
       r.nxt = r.via >= 0 ? r.via : r.to;
+      r.nxt_len = sc->lane_len[r.nxt]; r.nxt_vmax = sc->lane_vmax[r.nxt];
+      r.nxt_internal = sc->lane_internal[r.nxt]; r.from_internal = sc->lane_internal[r.from];
+      r.nxt_link = !r.nxt_internal ? -3 : (sc->lane_link_off[r.nxt] < sc->lane_link_off[r.nxt + 1] ? sc->lane_link_off[r.nxt] : -2);
+      r.yield_parent = -1; r.yield_cross = 0.0f;
+      if (r.from_internal) {
+        const int p = sc->link_parent[k];
+        if (p >= 0 && sc->link_cont[p] && sc->link_via[p] == r.from) {
+          r.yield_parent = p;
+          r.yield_cross = sc->link_via_len[p] - sc->lane_len[r.from];
+        }
+      }
+      r.foe_end = sc->link_foe_off[k + 1];
       int lo = 0x7FFFFFFF, hi = -1;
       for (int i = sc->link_foe_off[k]; i < sc->link_foe_off[k + 1]; ++i) {
         const int li = sc->link_last_int[sc->foe_link[i]];

@@ -63,7 +63,17 @@ struct alignas(16) LinkRec {
   // lane-occupancy bit array (Tile::occ), so "is somebody crossing my path" is two ANDs instead of a loop over
   // the foes; occ_word = -1 if the foes' lanes do not fit such a window (then the loop runs)
   int32_t occ_word; uint32_t occ_lo, occ_hi;
-};                                                   // 64 B; [n_links + 1] (sentinel carries foe_off = n_foes)
+  // what a hop of the junction look-ahead needs about the lanes on both sides of the link, joined in, so that a hop
+  // touches this record instead of three or four (on the big maps every table line is an L2 round trip: two 110 KB CTAs
+  // leave ~30 KB of L1 for 0.8 MB of tables)
+  float nxt_len, nxt_vmax;                           // lane_len / lane_vmax of nxt
+  int32_t nxt_internal, from_internal;               // lane_internal of nxt / of from
+  int32_t nxt_link;                                  // nxt internal: its one continuing link, or -2 if it has none; nxt normal: -3 (route lookup)
+  int32_t yield_parent;                              // from internal: the entry link whose foes are yielded to at this point
+                                                     // (parent with an internal junction whose waiting slot is `from`), else -1
+  float yield_cross;                                 // ... and its crossing distance without the vehicle length
+  int32_t foe_end;                                   // foe_off of the next link
+};                                                   // 96 B; [n_links + 1] (sentinel carries foe_off = n_foes)
 struct alignas(16) FoeRec {                          // one foe of a link, joined with what link_blocked reads of it
   int32_t link, flags, last_int, from;               // foe link f, foe_flags, link_last_int[f], link_from[f]
   int32_t slot /* link_cont[f] ? link_via[f] : -1 */; float via_len, len_from, len_slot;
@@ -299,7 +309,7 @@ __device__ __forceinline__ bool time_conflict(float seen, float v, float cross, 
 
 // right-of-way: must the vehicle on entry link k wait for one of its foes?
 RS_HEAVY bool link_blocked(const DevScenario& sc, const Tile& t, int k, float seen, float v, float cross) {
-  const int f0 = __ldg(&sc.link_rec[k].foe_off), f1 = __ldg(&sc.link_rec[k + 1].foe_off);
+  const int f0 = __ldg(&sc.link_rec[k].foe_off), f1 = __ldg(&sc.link_rec[k].foe_end);
   if (f0 >= f1) return false;
   const int4* rec = reinterpret_cast<const int4*>(sc.foe_rec);
   int4 a = __ldg(rec + 2 * f0);                          // {link, flags, last_int, from}
@@ -357,16 +367,15 @@ RS_HEAVY bool must_stop(const DevScenario& sc, const Tile& t, int i, int k, floa
   int vt = v_vtype(t, i);
   float len = VTT(t, vt, VT_LEN), decel = VTT(t, vt, VT_DECEL);
   float v = t.speed[i];
-  int from = __ldg(&sc.link_rec[k].from);
-  const bool from_internal = __ldg(&sc.lane_rec[from].internal) != 0;
+  const int4 jn = __ldg(reinterpret_cast<const int4*>(&sc.link_rec[k]) + 5);   // {nxt_link, yield_parent, yield_cross, foe_end}
+  const bool from_internal = __ldg(&sc.link_rec[k].from_internal) != 0;
   int yield_link = -1;          // entry link whose foes must be checked (one call site for link_blocked)
   float cross = 0.0f;
   int st = 0;
   if (from_internal) {
-    int p = __ldg(&sc.link_rec[k].parent);
-    if (!((hop == 0 || binds) && p >= 0 && __ldg(&sc.link_rec[p].cont) && __ldg(&sc.link_rec[p].via) == from)) return false;
-    yield_link = p;
-    cross = __ldg(&sc.link_rec[p].via_len) - __ldg(&sc.lane_rec[from].len) + len;
+    if (!((hop == 0 || binds) && jn.y >= 0)) return false;
+    yield_link = jn.y;
+    cross = __int_as_float(jn.z) + len;
   } else {
     st = state_now(sc, t, k);
     if (st == 'r' || st == 'u') return true;
@@ -381,7 +390,7 @@ RS_HEAVY bool must_stop(const DevScenario& sc, const Tile& t, int i, int k, floa
     if (from_internal) return b;
     if (b) return true;
   }
-  const int f0 = __ldg(&sc.link_rec[k].foe_off), f1 = __ldg(&sc.link_rec[k + 1].foe_off);
+  const int f0 = __ldg(&sc.link_rec[k].foe_off), f1 = jn.w;
   if (__ldg(&sc.link_rec[k].cont)) {
     // waiting slot inside the junction is taken by a STANDING vehicle (a moving one is simply followed)
     int vl = __ldg(&sc.link_rec[k].via);
@@ -479,8 +488,9 @@ RS_HEAVY void plan_vehicle(const DevScenario& sc, const Tile& t, int i, float& v
     // a lane end further away than the look-ahead distance plus the longest vehicle that could still stick
     // out of the junction cannot bind the speed: no junction logic at all
     const bool far = seen > la + 20.0f;
+    int knext = -3;   // link of the NEXT hop when the lane ahead is internal (joined into LinkRec), -3: route lookup
     for (int hop = 0; hop < kMaxHops && !far; ++hop) {
-      int k = hop == 0 ? v_nextlink(sc, t, i, lane) : next_link(sc, cur, route, cc);
+      int k = hop == 0 ? v_nextlink(sc, t, i, lane) : (knext != -3 ? knext : next_link(sc, cur, route, cc));
       if (k == -1) break;
       if (k == -2) {
         vsafe = fminf(vsafe, max_safe_stop_speed(seen, decel, tau));
@@ -490,7 +500,8 @@ RS_HEAVY void plan_vehicle(const DevScenario& sc, const Tile& t, int i, float& v
       const float vstop = max_safe_stop_speed(seen, decel, tau);
       if (must_stop(sc, t, i, k, seen, hop, cc, vstop < vsafe)) { vsafe = fminf(vsafe, vstop); break; }
       int nxt = __ldg(&sc.link_rec[k].nxt);
-      vsafe = fminf(vsafe, free_speed(decel, seen, fminf(__ldg(&sc.lane_rec[nxt].vmax) * sf, vcapv)));
+      const int4 nx = __ldg(reinterpret_cast<const int4*>(&sc.link_rec[k]) + 4);   // {nxt_len, nxt_vmax, nxt_internal, from_internal}
+      vsafe = fminf(vsafe, free_speed(decel, seen, fminf(__int_as_float(nx.y) * sf, vcapv)));
       if (lane_count(t, nxt) > 0) {
         int tl = (int)t.lane_start[nxt + 1] - 1, tvt = v_vtype(t, tl);
         float gap = seen + (t.pos[tl] - VTT(t, tvt, VT_LEN)) - mingap;
@@ -499,9 +510,10 @@ RS_HEAVY void plan_vehicle(const DevScenario& sc, const Tile& t, int i, float& v
         if (hop == 0) vlead_limit = fminf(vlead_limit, f);
         break;
       }
-      seen += __ldg(&sc.lane_rec[nxt].len);
-      if (!__ldg(&sc.lane_rec[nxt].internal)) cc += 1;
+      seen += __int_as_float(nx.x);
+      if (!nx.z) cc += 1;
       cur = nxt;
+      knext = __ldg(&sc.link_rec[k].nxt_link);
       if (seen > la) break;
     }
   }
