@@ -13,5 +13,9 @@ for c in ${@:-c2 c3 c5}; do
   SKIP=1; if [ $c = c3 ] || [ $c = c4 ]; then SKIP=2; fi
   ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:k_run -s $SKIP -c 1 -f -o $O/${T}_${c}_krun \
       python bench.py --config $c --steps 8 --warmup 3 --no-cpu --profile > $O/${T}_${c}_ncu.log 2>&1
-  ls -la $O/${T}_${c}_krun.ncu-rep
+  # gpurun merges at most 64 MiB back: keep the exports (raw page, per-instruction source page), not the 23 MB reports
+  ncu -i $O/${T}_${c}_krun.ncu-rep --page raw --csv > $O/${T}_${c}_raw.csv 2>/dev/null
+  ncu -i $O/${T}_${c}_krun.ncu-rep --page source --csv > $O/${T}_${c}_src.csv 2>/dev/null
+  rm -f $O/${T}_${c}_krun.ncu-rep
+  ls -la $O/${T}_${c}_raw.csv $O/${T}_${c}_src.csv
 done
