@@ -95,23 +95,6 @@ enum { M_NARR = 0, M_NOK, M_NAFTER, M_NDIRTY, M_NOKC, M_MAYDEFER /* outgrowing t
 
 constexpr int kDirty = 0x40000000;   // flag bit in cnt2[l]: the lane gained or lost a vehicle this tick
 
-// Experimental (build with -DRS_BALANCED_PLAN=1; NOT in the default build, A/B with tools/gpu_ab2.sh): CTA-wide work
-// lists for the plan phase.  Lane heads (junction look-ahead: expensive) and followers (cheap) of ALL instances of the
-// CTA are dealt round-robin to the warps, so that every warp plans the same number of expensive vehicles whatever
-// instance or lane they belong to.  Entry = instance slot << 12 | vehicle index.  Measured on cologne8 (8 x 64
-// threads): -1 % kernel time, every warp already holds a mix.  Meant for the big-map shape (one instance per 512
-// threads, vehicles lane-major, 41 % of the warp samples at the plan barrier: profiles/r01_krun_ncu_summary.md).
-#ifndef RS_BALANCED_PLAN
-#define RS_BALANCED_PLAN 0
-#endif
-#if RS_BALANCED_PLAN
-constexpr int kPlanListCap = 2048;
-__shared__ uint16_t s_plan_heavy[kPlanListCap];
-__shared__ uint16_t s_plan_light[kPlanListCap];
-__shared__ int s_plan_n[2];
-__shared__ uint32_t s_slot_env[16][2];     // global instance id (lo, hi) of each instance slot of the CTA
-#endif
-
 struct OriginCand { int32_t vid; uint16_t route; int16_t ok_dd; int32_t vt; };   // ok_dd: -1 not ok, -2 refused by capacity, else depart delay
 
 // ------------------------------------------------------------------------------------------------
@@ -150,16 +133,6 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
     T.tls_state[t] = __ldg(sc.phase_state_off + p0 + T.tls_phase[t]);
   }
   if (tid == 0) { misc[M_NARR] = 0; misc[M_NOK] = 0; misc[M_NDIRTY] = 0; misc[M_NOKC] = 0; }
-#if RS_BALANCED_PLAN
-  if (G <= 16) {   // the lists are only used if all vehicles of the CTA fit them (the counters keep counting past the capacity)
-    const int g = threadIdx.x / BLOCK;
-    for (int i = tid; i < n; i += BLOCK) {
-      const bool head = i == (int)T.lane_start[v_lane(T, i)];
-      const int slot = atomicAdd(&s_plan_n[head ? 0 : 1], 1);
-      if (slot < kPlanListCap) (head ? s_plan_heavy : s_plan_light)[slot] = (uint16_t)((g << 12) | i);
-    }
-  }
-#endif
   __syncthreads();
   PCLK(PC_S0);
 
@@ -170,41 +143,12 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
   };
 
   // ---- S1: plan (reads only start-of-tick state) ----
-#if RS_BALANCED_PLAN
-  bool dealt = false;
-  if (G <= 16) {
-    const int H = s_plan_n[0], Lt = s_plan_n[1];
-    if (H <= kPlanListCap && Lt <= kPlanListCap && m.vcap <= 4096) {
-      dealt = true;
-      const int W = (BLOCK * G) >> 5, w = threadIdx.x >> 5, l = threadIdx.x & 31, g = threadIdx.x / BLOCK;
-      const int hc = H > w ? (H - w + W - 1) / W : 0, lc = Lt > w ? (Lt - w + W - 1) / W : 0;
-      for (int p = l; p < hc + lc; p += 32) {
-        const uint32_t item = p < hc ? s_plan_heavy[w + p * W] : s_plan_light[w + (p - hc) * W];
-        const int g2 = (int)(item >> 12), i = (int)(item & 0xFFFu);
-        const ptrdiff_t delta = (ptrdiff_t)(g2 - g) * (ptrdiff_t)m.total;
-        tile_shift(T, delta);
-        const uint32_t elo = T.env_lo, ehi = T.env_hi;
-        T.env_lo = s_slot_env[g2][0]; T.env_hi = s_slot_env[g2][1];
-        float v; int tg;
-        plan_vehicle(sc, T, i, v, tg);
-        *(float*)((unsigned char*)(vn + i) + delta) = v;
-        *(uint16_t*)((unsigned char*)(newlane + i) + delta) = (uint16_t)tg;
-        tile_shift(T, -delta);
-        T.env_lo = elo; T.env_hi = ehi;
-      }
-    }
-  }
-  if (!dealt)
-#endif
   for (int i = tid; i < n; i += BLOCK) {
     float v; int tg;
     plan_vehicle(sc, T, i, v, tg);
     vn[i] = v; newlane[i] = (uint16_t)tg;
   }
   __syncthreads();
-#if RS_BALANCED_PLAN
-  if (G <= 16 && threadIdx.x == 0) { s_plan_n[0] = 0; s_plan_n[1] = 0; }   // next use: S0 of the next tick, barriers away
-#endif
   PCLK(PC_S1);
 
   // ---- S2: move: update in place, hand-off across lanes, bucket movers by target lane ----
@@ -675,12 +619,6 @@ __device__ __forceinline__ bool run_instance(const DevSim& D, const RunArgs& A, 
   T.occ = (const uint32_t*)(smem + m.off_occ);
   const uint64_t env_id = (uint64_t)(D.first_env_id + env);
   T.env_lo = (uint32_t)env_id; T.env_hi = (uint32_t)(env_id >> 32);
-#if RS_BALANCED_PLAN
-  if (G <= 16 && tid == 0) {
-    s_slot_env[threadIdx.x / BLOCK][0] = T.env_lo; s_slot_env[threadIdx.x / BLOCK][1] = T.env_hi;
-    if (threadIdx.x == 0) { s_plan_n[0] = 0; s_plan_n[1] = 0; }
-  }
-#endif
   T.seed_lo = (uint32_t)D.seed; T.seed_hi = (uint32_t)(D.seed >> 32);
 
   // ---- stage the instance tile: HBM -> shared (128-bit coalesced loads) ----

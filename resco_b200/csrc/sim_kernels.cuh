@@ -232,18 +232,6 @@ __device__ __forceinline__ void tile_bind(Tile& t, uint32_t* base, int vcap) {
   t.aw = base + 10 * vcap;
 }
 
-// re-point the view at the tile of another instance slot of the same CTA (`delta` bytes away in shared memory); all
-// slots share one layout and, stepping in lock-step, the same ping-pong parity (RS_BALANCED_PLAN experiment in sim.cu)
-template <typename P> __device__ __forceinline__ void ptr_shift(P*& p, ptrdiff_t delta) {
-  p = (P*)((unsigned char*)p + delta);
-}
-__device__ __forceinline__ void tile_shift(Tile& t, ptrdiff_t delta) {
-  ptr_shift(t.pos, delta); ptr_shift(t.speed, delta); ptr_shift(t.sf, delta); ptr_shift(t.tloss, delta);
-  ptr_shift(t.vid, delta); ptr_shift(t.wr, delta); ptr_shift(t.rc, delta); ptr_shift(t.meta, delta);
-  ptr_shift(t.ed, delta); ptr_shift(t.dl, delta); ptr_shift(t.aw, delta); ptr_shift(t.lane_start, delta); ptr_shift(t.tls_phase, delta);
-  ptr_shift(t.tls_end, delta); ptr_shift(t.tls_state, delta); ptr_shift(t.occ, delta); ptr_shift(t.vt, delta);
-}
-
 #define VTT(t, i, f) ((t).vt[(i) * 8 + (f)])
 __device__ __forceinline__ int v_vtype(const Tile& t, int i) { return (int)(t.meta[i] & 0xFFu); }
 __device__ __forceinline__ int v_lcc(const Tile& t, int i) { return (int)((t.meta[i] >> 8) & 0xFFu); }
