@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define RS_ABI_VERSION 4
+#define RS_ABI_VERSION 5
 #define RS_N_MOVEMENTS 12   /* the 12 movement keys of signal_config.py lane_sets */
 
 typedef enum RsStatus {
@@ -106,6 +106,9 @@ typedef struct RsScenario {
   const int32_t* trip_route;
   const int32_t* trip_vtype;
   const int32_t* trip_file;          /* index in the route file (tripinfo order) */
+  const int32_t* trip_depart_pos;    /* 0: departPos="base" (back of the origin lane); 1: departPos="random_free" (arterial4x4's
+                                      * route files): up to ten random positions on the origin lane are tried for one
+                                      * where the vehicle fits between its neighbours, then the base rule */
   /* synthetic Bernoulli-per-tick demand; used when synthetic != 0 */
   const int32_t* origin_rate;        /* P(insert request per tick) * 2^24 */
   const int32_t* origin_route_off;   /* [n_origins+1] into origin_route */

@@ -100,7 +100,7 @@ static void philox(uint32_t c[4], uint32_t k0, uint32_t k1) {
 }
 void orc_philox(uint32_t* ctr_inout, uint32_t k0, uint32_t k1) { philox(ctr_inout, k0, k1); }
 
-enum { STREAM_SF = 1, STREAM_DAWDLE = 2, STREAM_DEMAND = 3, STREAM_ROUTE = 4 };
+enum { STREAM_SF = 1, STREAM_DAWDLE = 2, STREAM_DEMAND = 3, STREAM_ROUTE = 4, STREAM_DEPARTPOS = 5 };
 
 static void rng4(const OrcSim* s, const Inst* in, uint32_t stream, uint32_t a, uint32_t b, uint32_t out[4]) {
   out[0] = (uint32_t)in->env_id; out[1] = (uint32_t)(in->env_id >> 32); out[2] = a; out[3] = b;
@@ -518,6 +518,30 @@ static void plan_vehicle(const OrcSim* s, Inst* in, int i, int lane, int rank) {
   in->new_lane[i] = target >= 0 ? target : lane;
 }
 
+/* insertion safety against the heads of the lanes upstream of origin `o` (within the compiled reach): nobody who is
+ * about to drive onto `lane` may be forced into hard braking by a vehicle standing with its back `back` metres in */
+static int upstream_clear(const OrcSim* s, const Inst* in, int o, int lane, float back) {
+  const RsScenario* sc = &s->sc;
+  for (int w = sc->origin_watch_off[o]; w < sc->origin_watch_off[o + 1]; ++w) {
+    int pl = sc->origin_watch_lane[w];
+    if (in->lane_start2[pl + 1] <= in->lane_start2[pl]) continue;
+    const Veh* h = &in->veh2[in->lane_start2[pl]];
+    int cur = pl, cc = h->cursor, reaches = 0;
+    for (int hop = 0; hop < 4; ++hop) {
+      int k = choose_link(sc, cur, h->route, cc);
+      if (k < 0) break;
+      int nxt = sc->link_via[k] >= 0 ? sc->link_via[k] : sc->link_to[k];
+      if (nxt == lane) { reaches = 1; break; }
+      if (!sc->lane_internal[nxt]) cc += 1;
+      cur = nxt;
+    }
+    if (!reaches) continue;
+    float gap = ((sc->lane_len[pl] - h->pos) + sc->origin_watch_dist[w] - VT(s, h->vtype, VT_GAP)) + back;
+    if (gap < brake_gap(h->speed, VT(s, h->vtype, VT_DECEL), VT(s, h->vtype, VT_TAU))) return 0;
+  }
+  return 1;
+}
+
 static int cmp_mover(const Inst* in, int a, int b) {
   float xa = in->new_pos[a], xb = in->new_pos[b];
   if (xa > xb) return -1;
@@ -647,6 +671,7 @@ static void tick_instance(OrcSim* s, Inst* in) {
     int* add = (int*)calloc((size_t)L1, sizeof(int));
     Veh* newv = (Veh*)malloc(sizeof(Veh) * (size_t)(sc->n_origins > 0 ? sc->n_origins : 1));
     int* newl = (int*)malloc(sizeof(int) * (size_t)(sc->n_origins > 0 ? sc->n_origins : 1));
+    int* newr = (int*)malloc(sizeof(int) * (size_t)(sc->n_origins > 0 ? sc->n_origins : 1));
     int nn = 0;
     int n_after_move = in->lane_start2[L];
     for (int o = 0; o < sc->n_origins; ++o) {
@@ -672,40 +697,54 @@ static void tick_instance(OrcSim* s, Inst* in) {
         ddelay = in->tick - (int)sc->trip_depart[c];
       }
       float len = VT(s, vt, VT_LEN), mingap = VT(s, vt, VT_GAP);
-      int ok = len <= sc->lane_len[lane];
       int a = in->lane_start2[lane], b = in->lane_start2[lane + 1];
-      if (ok && b > a) {
-        const Veh* tl = &in->veh2[b - 1];
-        if (tl->pos - VT(s, tl->vtype, VT_LEN) - len - mingap < 0.0f) ok = 0;
-      }
-      /* upstream safety: nobody who is about to drive onto this lane may be forced into hard braking */
-      for (int w = sc->origin_watch_off[o]; ok && w < sc->origin_watch_off[o + 1]; ++w) {
-        int pl = sc->origin_watch_lane[w];
-        if (in->lane_start2[pl + 1] <= in->lane_start2[pl]) continue;
-        const Veh* h = &in->veh2[in->lane_start2[pl]];
-        int cur = pl, cc = h->cursor, reaches = 0;
-        for (int hop = 0; hop < 4; ++hop) {
-          int k = choose_link(sc, cur, h->route, cc);
-          if (k < 0) break;
-          int nxt = sc->link_via[k] >= 0 ? sc->link_via[k] : sc->link_to[k];
-          if (nxt == lane) { reaches = 1; break; }
-          if (!sc->lane_internal[nxt]) cc += 1;
-          cur = nxt;
+      int ok = 0, rank = -1;        /* rank: vehicles of the lane ahead of the newcomer; -1 = it goes to the back */
+      float ipos = len;
+      /* departPos="random_free" (arterial4x4's route files): SUMO tries ten uniformly drawn positions for one where the
+       * vehicle fits (MSLane::insertVehicle, RANDOM_FREE), then falls back to a free insertion -- here the base rule.
+       * A position fits when no vehicle of the lane ahead of it is closer than the minimum gap and none behind it
+       * (on the lane, else the upstream heads) would have to brake hard for a standing vehicle at that place. */
+      if (!sc->synthetic && sc->trip_depart_pos[vid] == 1 && len <= sc->lane_len[lane]) {
+        for (int k = 0; k < 10 && !ok; ++k) {
+          uint32_t r[4];
+          rng4(s, in, STREAM_DEPARTPOS, (uint32_t)vid, (uint32_t)in->tick * 4u + (uint32_t)(k >> 2), r);
+          float u = (float)(r[k & 3] >> 8) * (1.0f / 16777216.0f);
+          float p = len + u * (sc->lane_len[lane] - len);
+          float back = p - len;
+          int fits = 1, ahead = 0, behind = 0;
+          for (int i = a; i < b; ++i) {
+            const Veh* x = &in->veh2[i];
+            if (x->pos >= p) {
+              ahead += 1;
+              if (x->pos - VT(s, x->vtype, VT_LEN) - p - mingap < 0.0f) fits = 0;
+            } else {
+              behind += 1;
+              if (back - x->pos - VT(s, x->vtype, VT_GAP) < brake_gap(x->speed, VT(s, x->vtype, VT_DECEL), VT(s, x->vtype, VT_TAU))) fits = 0;
+            }
+          }
+          if (fits && behind == 0) fits = upstream_clear(s, in, o, lane, back);
+          if (fits) { ok = 1; rank = ahead; ipos = p; }
         }
-        if (!reaches) continue;
-        float gap = (sc->lane_len[pl] - h->pos) + sc->origin_watch_dist[w] - VT(s, h->vtype, VT_GAP);
-        if (gap < brake_gap(h->speed, VT(s, h->vtype, VT_DECEL), VT(s, h->vtype, VT_TAU))) ok = 0;
+      }
+      if (!ok) {
+        ok = len <= sc->lane_len[lane];
+        if (ok && b > a) {
+          const Veh* tl = &in->veh2[b - 1];
+          if (tl->pos - VT(s, tl->vtype, VT_LEN) - len - mingap < 0.0f) ok = 0;
+        }
+        /* upstream safety: nobody who is about to drive onto this lane may be forced into hard braking */
+        if (ok) ok = upstream_clear(s, in, o, lane, 0.0f);
       }
       /* capacity of the vehicle store: an insertion the road has room for but the store does not is put off and COUNTED
        * (SUMO has no such limit; a non-zero count means the run was truncated by `vcap`) */
       if (ok && !((n_after_move + nn) < sc->vcap)) { ok = 0; in->st.n_cap_refused += 1; }
       if (ok) {
         Veh nv; memset(&nv, 0, sizeof nv);
-        nv.pos = len; nv.speed = 0.0f; nv.vid = vid; nv.vtype = vt; nv.route = route; nv.cursor = 0;
+        nv.pos = ipos; nv.speed = 0.0f; nv.vid = vid; nv.vtype = vt; nv.route = route; nv.cursor = 0;
         nv.depart = in->tick; nv.ddelay = ddelay; nv.seen_epoch = -2; nv.seen_sig = -1;
         float dev = sc->speed_dev_override >= 0.0f ? sc->speed_dev_override : VT(s, vt, VT_DEV);
         nv.sf = speed_factor(s, in, vid, dev);
-        newv[nn] = nv; newl[nn] = lane; add[lane] += 1; ++nn;
+        newv[nn] = nv; newl[nn] = lane; newr[nn] = rank; add[lane] += 1; ++nn;
         in->origin_cur[o] += 1;
         if (sc->synthetic) in->origin_backlog[o] -= 1;
         in->st.n_inserted += 1;
@@ -716,13 +755,18 @@ static void tick_instance(OrcSim* s, Inst* in) {
     for (int l = 0; l < L; ++l) {
       int a = in->lane_start2[l], b = in->lane_start2[l + 1];
       in->lane_start[l] = w;
-      for (int i = a; i < b; ++i) in->veh[w++] = in->veh2[i];
+      int at = -1, nq = -1;      /* one origin per lane: at most one newcomer, at its rank or at the back */
       if (add[l])
-        for (int q = 0; q < nn; ++q) if (newl[q] == l) in->veh[w++] = newv[q];
+        for (int q = 0; q < nn; ++q) if (newl[q] == l) { nq = q; at = newr[q] < 0 ? b : a + newr[q]; }
+      for (int i = a; i < b; ++i) {
+        if (i == at) in->veh[w++] = newv[nq];
+        in->veh[w++] = in->veh2[i];
+      }
+      if (at == b) in->veh[w++] = newv[nq];
     }
     in->lane_start[L] = w;
     in->n_veh = w;
-    free(add); free(newv); free(newl);
+    free(add); free(newv); free(newl); free(newr);
   }
   if (getenv("ORC_TRACE")) {   /* diagnostic: ORC_TRACE="vidA,vidB" prints both vehicles every tick */
     int va = -1, vb = -1;
@@ -889,7 +933,7 @@ OrcSim* orc_create(const RsScenario* sc, int32_t n_env, uint64_t seed) {
   DUP(route_off, sc->n_routes + 1, int32_t); DUP(route_edge, sc->n_route_steps, int32_t); DUP(route_mask, sc->n_route_steps, int32_t);
   DUP(origin_lane, sc->n_origins, int32_t); DUP(origin_off, sc->n_origins + 1, int32_t);
   DUP(trip_depart, sc->n_trips, float); DUP(trip_route, sc->n_trips, int32_t); DUP(trip_vtype, sc->n_trips, int32_t);
-  DUP(trip_file, sc->n_trips, int32_t);
+  DUP(trip_file, sc->n_trips, int32_t); DUP(trip_depart_pos, sc->n_trips, int32_t);
   DUP(origin_rate, sc->n_origins, int32_t); DUP(origin_route_off, sc->n_origins + 1, int32_t);
   DUP(origin_route, sc->n_origin_routes, int32_t);
   DUP(origin_watch_off, sc->n_origins + 1, int32_t); DUP(origin_watch_lane, sc->n_watch, int32_t); DUP(origin_watch_dist, sc->n_watch, float); DUP(origin_watch_owner, sc->n_watch, int32_t);

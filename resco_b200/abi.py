@@ -12,7 +12,7 @@ import numpy as np
 
 from .scenario.compiler import Scenario, green_phase_indices
 
-RS_ABI_VERSION = 4
+RS_ABI_VERSION = 5
 
 _I32P = C.POINTER(C.c_int32)
 _F32P = C.POINTER(C.c_float)
@@ -39,7 +39,7 @@ _PTRS: List[Tuple[str, object]] = [
     ("out_slot", _I32P),
     ("vtype", _F32P), ("vtype_bit", _I32P), ("route_off", _I32P), ("route_edge", _I32P),
     ("route_mask", _I32P), ("origin_lane", _I32P), ("origin_off", _I32P), ("trip_depart", _F32P),
-    ("trip_route", _I32P), ("trip_vtype", _I32P), ("trip_file", _I32P),
+    ("trip_route", _I32P), ("trip_vtype", _I32P), ("trip_file", _I32P), ("trip_depart_pos", _I32P),
     ("origin_rate", _I32P), ("origin_route_off", _I32P), ("origin_route", _I32P),
     ("origin_watch_off", _I32P), ("origin_watch_lane", _I32P), ("origin_watch_dist", _F32P),
     ("origin_watch_owner", _I32P),
@@ -257,8 +257,10 @@ def marshal(sc: Scenario, *, step_length: int = 10, yellow_length: int = 3, max_
             sizes["n_vtypes"] = len(synthetic["vtype_bit"])
         for nm in ("trip_depart",):
             arrays[nm] = (np.zeros(1, np.float32), np.float32)
-        for nm in ("trip_route", "trip_vtype", "trip_file"):
+        for nm in ("trip_route", "trip_vtype", "trip_file", "trip_depart_pos"):
             arrays[nm] = (np.zeros(1, np.int32), np.int32)
+    if "trip_depart_pos" not in arrays:        # scenarios compiled before the field existed: departPos="base" everywhere
+        arrays["trip_depart_pos"] = (np.zeros(max(n_trips, 1), np.int32), np.int32)
     for k, v in sizes.items():
         setattr(st, k, int(v))
     for name, ct in _PTRS:
@@ -308,7 +310,7 @@ def smem_bytes(vcap: int, n_lanes: int, n_tls: int, n_signals: int, n_origins: i
     o = al(o + max(n_signals, 1) * 4)
     o = al(o + max(n_origins, 1) * 4)
     o = al(o + max(n_origins, 1) * 4)
-    o = al(o + max(n_origins, 1) * 12)
+    o = al(o + max(n_origins, 1) * 16)
     o = al(o + n_vtypes * 32)
     o = al(o + 16 * 4)
     o = al(o + 48 * 4)

@@ -58,7 +58,7 @@ __host__ __device__ inline SmemLayout make_layout_ex(const DevScenario& sc, int 
   m.off_next_phase = o; o = align16(o + (size_t)(m.S > 0 ? m.S : 1) * 4);
   m.off_origin_cur = o; o = align16(o + (size_t)(m.O > 0 ? m.O : 1) * 4);
   m.off_origin_backlog = o; o = align16(o + (size_t)(m.O > 0 ? m.O : 1) * 4);
-  m.off_origin_cand = o; o = align16(o + (size_t)(m.O > 0 ? m.O : 1) * 12);
+  m.off_origin_cand = o; o = align16(o + (size_t)(m.O > 0 ? m.O : 1) * 16);
   m.off_vt = o; o = align16(o + (size_t)m.n_vt * 8 * 4);
   m.off_hdr = o; o = align16(o + (size_t)kHdrInts * 4);
   m.off_misc = o; o = align16(o + 48 * 4);
@@ -95,7 +95,11 @@ enum { M_NARR = 0, M_NOK, M_NAFTER, M_NDIRTY, M_NOKC, M_MAYDEFER /* outgrowing t
 
 constexpr int kDirty = 0x40000000;   // flag bit in cnt2[l]: the lane gained or lost a vehicle this tick
 
-struct OriginCand { int32_t vid; uint16_t route; int16_t ok_dd; int32_t vt; };   // ok_dd: -1 not ok, -2 refused by capacity, else depart delay
+// ok_dd: -1 not ok, -2 refused by capacity, else depart delay; rank: vehicles of the lane ahead of the newcomer
+// (departPos="random_free"), kRankBack = it goes to the back of the lane (departPos="base"); pos: its front position
+struct OriginCand { int32_t vid; uint16_t route; int16_t ok_dd; uint16_t vt; uint16_t rank; float pos; };
+static_assert(sizeof(OriginCand) == 16, "OriginCand is 16 bytes in the shared-memory layout");
+constexpr uint32_t kRankBack = 0xFFFFu;
 
 // ------------------------------------------------------------------------------------------------
 template <int BLOCK, int G>
@@ -232,8 +236,8 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
     // so an origin with nothing due costs one shared-memory compare
     if (!sc.synthetic && !(__int_as_float(origin_backlog[o]) <= (float)T.tick)) { cand[o].ok_dd = -1; continue; }
     int lane = __ldg(sc.origin_lane + o);
-    OriginCand c; c.ok_dd = -1; c.route = 0; c.vt = 0; c.vid = 0;
-    bool have = false;
+    OriginCand c; c.ok_dd = -1; c.route = 0; c.vt = 0; c.vid = 0; c.rank = (uint16_t)kRankBack; c.pos = 0.0f;
+    bool have = false, rnd = false;
     int dd = 0;
     if (sc.synthetic) {
       uint32_t r[4];
@@ -245,7 +249,7 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
         else {
           rng4(T, STREAM_ROUTE, (uint32_t)o, (uint32_t)origin_cur[o], r);
           c.route = __ldg(sc.origin_route + r0 + (int)(r[0] % (uint32_t)nr));
-          c.vt = sc.synthetic_vtype;
+          c.vt = (uint16_t)sc.synthetic_vtype;
           c.vid = (o << 16) | (origin_cur[o] & 0xFFFF);
           have = true;
         }
@@ -253,57 +257,89 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
     } else {
       int ci = __ldg(sc.origin_off + o) + origin_cur[o];
       if (ci < __ldg(sc.origin_off + o + 1) && !(__ldg(sc.trip_depart + ci) > (float)T.tick)) {
-        c.route = __ldg(sc.trip_route + ci); c.vt = __ldg(sc.trip_vtype + ci); c.vid = ci;
+        c.route = __ldg(sc.trip_route + ci); c.vt = (uint16_t)__ldg(sc.trip_vtype + ci); c.vid = ci;
         dd = T.tick - (int)__ldg(sc.trip_depart + ci);
+        rnd = __ldg(sc.trip_depart_pos + ci) == 1;
         have = true;
       }
     }
     if (have) {
-      float len = VTT(T, c.vt, VT_LEN), mingap = VTT(T, c.vt, VT_GAP);
-      bool ok = len <= __ldg(&sc.lane_rec[lane].len);
-      if (ok) {
-        // post-move tail of the origin lane = last element of the merged (stayers + movers) order
-        int a = T.lane_start[lane], b = T.lane_start[lane + 1];
-        int ls = -1;
-        for (int i = b - 1; i >= a; --i) if (newlane[i] == lane) { ls = i; break; }
-        int tailv = ls;
-        int best = -1;   // mover with the smallest (pos, then largest idx)
-        for (int q = mhead[lane]; q >= 0; q = (mnext[q] == 0xFFFF ? -1 : (int)mnext[q]))
-          if (best < 0 || T.pos[q] < T.pos[best] || (T.pos[q] == T.pos[best] && q > best)) best = q;
-        if (best >= 0 && (ls < 0 || !(T.pos[best] > T.pos[ls]))) tailv = best;
-        if (tailv >= 0) {
-          int tvt = v_vtype(T, tailv);
-          if (T.pos[tailv] - VTT(T, tvt, VT_LEN) - len - mingap < 0.0f) ok = false;
+      const float len = VTT(T, c.vt, VT_LEN), mingap = VTT(T, c.vt, VT_GAP);
+      const float lane_len = __ldg(&sc.lane_rec[lane].len);
+      const int la = T.lane_start[lane], lb = T.lane_start[lane + 1];
+      // upstream safety: nobody who is about to drive onto this lane may be forced into hard braking by a vehicle
+      // standing with its back `back` metres into the lane
+      auto upstream_clear = [&](float back) {
+        for (int w = __ldg(sc.origin_watch_off + o); w < __ldg(sc.origin_watch_off + o + 1); ++w) {
+          int pl = __ldg(sc.origin_watch_lane + w);
+          // post-move head of pl: first stayer of the old segment vs. the front-most mover into pl
+          int a = T.lane_start[pl], b = T.lane_start[pl + 1];
+          int hs = -1;
+          for (int i = a; i < b; ++i) if (newlane[i] == pl) { hs = i; break; }
+          int hm = -1;
+          for (int q = mhead[pl]; q >= 0; q = (mnext[q] == 0xFFFF ? -1 : (int)mnext[q]))
+            if (hm < 0 || T.pos[q] > T.pos[hm] || (T.pos[q] == T.pos[hm] && q < hm)) hm = q;
+          int h = hs;
+          if (hm >= 0 && (hs < 0 || T.pos[hm] > T.pos[hs])) h = hm;
+          if (h < 0) continue;
+          // cheap test first: only a head that could not brake in time is worth the route look-ahead
+          int hvt = v_vtype(T, h);
+          float gap = ((__ldg(&sc.lane_rec[pl].len) - T.pos[h]) + __ldg(sc.origin_watch_dist + w) - VTT(T, hvt, VT_GAP)) + back;
+          if (!(gap < brake_gap(T.speed[h], VTT(T, hvt, VT_DECEL), VTT(T, hvt, VT_TAU)))) continue;
+          int cur = pl, cc = v_cursor(T, h), hr = v_route(T, h);
+          bool reaches = false;
+          for (int hop = 0; hop < 4; ++hop) {
+            int k = hop == 0 ? v_nextlink(sc, T, h, pl) : next_link(sc, cur, hr, cc);
+            if (k < 0) break;
+            int nxt = __ldg(&sc.link_rec[k].nxt);
+            if (nxt == lane) { reaches = true; break; }
+            if (!__ldg(&sc.lane_rec[nxt].internal)) cc += 1;
+            cur = nxt;
+          }
+          if (reaches) return false;
+        }
+        return true;
+      };
+      bool ok = false;
+      c.pos = len;
+      // departPos="random_free": ten uniformly drawn positions are tried for one where the vehicle fits between the
+      // post-move content of the lane (stayers of the old segment + movers chained at mhead), then the base rule
+      if (rnd && len <= lane_len) {
+        for (int k = 0; k < 10 && !ok; ++k) {
+          uint32_t r[4];
+          rng4(T, STREAM_DEPARTPOS, (uint32_t)c.vid, (uint32_t)T.tick * 4u + (uint32_t)(k >> 2), r);
+          const float u = (float)(r[k & 3] >> 8) * (1.0f / 16777216.0f);
+          const float p = len + u * (lane_len - len);
+          const float back = p - len;
+          bool fits = true; int ahead = 0, behind = 0;
+          auto look = [&](int i) {
+            const float x = T.pos[i]; const int xvt = v_vtype(T, i);
+            if (x >= p) { ahead += 1; if (x - VTT(T, xvt, VT_LEN) - p - mingap < 0.0f) fits = false; }
+            else { behind += 1; if (back - x - VTT(T, xvt, VT_GAP) < brake_gap(T.speed[i], VTT(T, xvt, VT_DECEL), VTT(T, xvt, VT_TAU))) fits = false; }
+          };
+          for (int i = la; i < lb; ++i) if (newlane[i] == lane) look(i);
+          for (int q = mhead[lane]; q >= 0; q = (mnext[q] == 0xFFFF ? -1 : (int)mnext[q])) look(q);
+          if (fits && behind == 0) fits = upstream_clear(back);
+          if (fits) { ok = true; c.rank = (uint16_t)ahead; c.pos = p; }
         }
       }
-      // upstream safety: nobody who is about to drive onto this lane may be forced into hard braking
-      for (int w = __ldg(sc.origin_watch_off + o); ok && w < __ldg(sc.origin_watch_off + o + 1); ++w) {
-    int pl = __ldg(sc.origin_watch_lane + w);
-      // post-move head of pl: first stayer of the old segment vs. the front-most mover into pl
-      int a = T.lane_start[pl], b = T.lane_start[pl + 1];
-      int hs = -1;
-      for (int i = a; i < b; ++i) if (newlane[i] == pl) { hs = i; break; }
-      int hm = -1;
-      for (int q = mhead[pl]; q >= 0; q = (mnext[q] == 0xFFFF ? -1 : (int)mnext[q]))
-        if (hm < 0 || T.pos[q] > T.pos[hm] || (T.pos[q] == T.pos[hm] && q < hm)) hm = q;
-      int h = hs;
-      if (hm >= 0 && (hs < 0 || T.pos[hm] > T.pos[hs])) h = hm;
-      if (h < 0) continue;
-      // cheap test first: only a head that could not brake in time is worth the route look-ahead
-      int hvt = v_vtype(T, h);
-      float gap = (__ldg(&sc.lane_rec[pl].len) - T.pos[h]) + __ldg(sc.origin_watch_dist + w) - VTT(T, hvt, VT_GAP);
-      if (!(gap < brake_gap(T.speed[h], VTT(T, hvt, VT_DECEL), VTT(T, hvt, VT_TAU)))) continue;
-      int cur = pl, cc = v_cursor(T, h), hr = v_route(T, h);
-      bool reaches = false;
-      for (int hop = 0; hop < 4; ++hop) {
-        int k = hop == 0 ? v_nextlink(sc, T, h, pl) : next_link(sc, cur, hr, cc);
-        if (k < 0) break;
-        int nxt = __ldg(&sc.link_rec[k].nxt);
-        if (nxt == lane) { reaches = true; break; }
-        if (!__ldg(&sc.lane_rec[nxt].internal)) cc += 1;
-        cur = nxt;
-      }
-      if (reaches) ok = false;
+      if (!ok) {
+        ok = len <= lane_len;
+        if (ok) {
+          // post-move tail of the origin lane = last element of the merged (stayers + movers) order
+          int ls = -1;
+          for (int i = lb - 1; i >= la; --i) if (newlane[i] == lane) { ls = i; break; }
+          int tailv = ls;
+          int best = -1;   // mover with the smallest (pos, then largest idx)
+          for (int q = mhead[lane]; q >= 0; q = (mnext[q] == 0xFFFF ? -1 : (int)mnext[q]))
+            if (best < 0 || T.pos[q] < T.pos[best] || (T.pos[q] == T.pos[best] && q > best)) best = q;
+          if (best >= 0 && (ls < 0 || !(T.pos[best] > T.pos[ls]))) tailv = best;
+          if (tailv >= 0) {
+            int tvt = v_vtype(T, tailv);
+            if (T.pos[tailv] - VTT(T, tvt, VT_LEN) - len - mingap < 0.0f) ok = false;
+          }
+        }
+        if (ok) ok = upstream_clear(0.0f);
       }
       if (ok) { c.ok_dd = dd; int s = atomicAdd(&misc[M_NOKC], 1); oklist[s] = (uint16_t)o; atomicAdd(&misc[M_NOK], 1); }
     }
@@ -367,13 +403,20 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
       }
       return best;
     };
+    // a newcomer placed between the vehicles of the lane (departPos="random_free") keeps the slot of its rank free
+    int hole = -1;
+    for (int j = 0; j < nokc; ++j) {
+      const int o = oklist[j];
+      if (cand[o].ok_dd >= 0 && cand[o].rank != kRankBack && __ldg(sc.origin_lane + o) == l) hole = w + (int)cand[o].rank;
+    }
     int mv = head >= 0 ? next_mover(ppos, pidx) : -1;
     for (int i = a; i < b; ++i) {
       if (newlane[i] != l) continue;
-      while (mv >= 0 && T.pos[mv] > T.pos[i]) { newidx[mv] = (uint16_t)w++; mv = next_mover(T.pos[mv], mv); }
+      while (mv >= 0 && T.pos[mv] > T.pos[i]) { w += (w == hole); newidx[mv] = (uint16_t)w++; mv = next_mover(T.pos[mv], mv); }
+      w += (w == hole);
       newidx[i] = (uint16_t)w++;
     }
-    while (mv >= 0) { newidx[mv] = (uint16_t)w++; mv = next_mover(T.pos[mv], mv); }
+    while (mv >= 0) { w += (w == hole); newidx[mv] = (uint16_t)w++; mv = next_mover(T.pos[mv], mv); }
   }
   __syncthreads();
   PCLK(PC_S5);
@@ -424,9 +467,9 @@ __device__ __forceinline__ void tick_body(const DevSim& D, const SmemLayout& m, 
       OriginCand c = cand[o];
       if (c.ok_dd < 0) continue;
       int lane = __ldg(sc.origin_lane + o);
-      int d = (int)start2[lane + 1] - 1;
+      int d = c.rank == kRankBack ? (int)start2[lane + 1] - 1 : (int)start2[lane] + (int)c.rank;
       float dev = sc.speed_dev_override >= 0.0f ? sc.speed_dev_override : VTT(T, c.vt, VT_DEV);
-      U.pos[d] = VTT(T, c.vt, VT_LEN); U.speed[d] = 0.0f; U.sf[d] = speed_factor(T, c.vid, dev); U.tloss[d] = 0.0f;
+      U.pos[d] = c.pos; U.speed[d] = 0.0f; U.sf[d] = speed_factor(T, c.vid, dev); U.tloss[d] = 0.0f;
       U.vid[d] = c.vid; U.wr[d] = 0u; U.rc[d] = (uint32_t)c.route;
       U.meta[d] = (uint32_t)c.vt | (0xFFu << 16) | (encode_nextlink(sc, lane, choose_link(sc, lane, c.route, 0)) << 24);
       U.ed[d] = 0xFFFEu | ((uint32_t)T.tick << 16);
@@ -1127,6 +1170,14 @@ extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, ui
       seen[l] = 1;
     }
   }
+  {   // one origin per lane: a tick inserts at most one vehicle into a lane
+    std::vector<char> seen((size_t)sc->n_lanes, 0);
+    for (int o = 0; o < sc->n_origins; ++o) {
+      const int l = sc->origin_lane[o];
+      if (l < 0 || l >= sc->n_lanes || seen[l]) return fail(RS_ERR_INVALID, "rs_create: a lane is listed twice in origin_lane");
+      seen[l] = 1;
+    }
+  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
     return fail(RS_ERR_NODEVICE, "rs_create: no CUDA device (this backend has no CPU fallback)");
@@ -1259,6 +1310,7 @@ extern "C" int rs_create(const RsScenario* sc, int32_t n_env, int32_t device, ui
   TRY(dev_dup(s, d.origin_lane, sc->n_origins)); TRY(dev_dup(s, d.origin_off, sc->n_origins + 1));
   TRY(dev_dup(s, d.trip_depart, sc->n_trips)); TRY(dev_dup(s, d.trip_route, sc->n_trips));
   TRY(dev_dup(s, d.trip_vtype, sc->n_trips)); TRY(dev_dup(s, d.trip_file, sc->n_trips));
+  TRY(dev_dup(s, d.trip_depart_pos, sc->n_trips));
   TRY(dev_dup(s, d.origin_rate, sc->n_origins)); TRY(dev_dup(s, d.origin_route_off, sc->n_origins + 1));
   TRY(dev_dup(s, d.origin_route, sc->n_origin_routes));
   TRY(dev_dup(s, d.origin_watch_off, sc->n_origins + 1)); TRY(dev_dup(s, d.origin_watch_lane, sc->n_watch));

@@ -162,7 +162,7 @@ __device__ __forceinline__ void philox(uint32_t c[4], uint32_t k0, uint32_t k1) 
     c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
   }
 }
-enum { STREAM_SF = 1, STREAM_DAWDLE = 2, STREAM_DEMAND = 3, STREAM_ROUTE = 4 };
+enum { STREAM_SF = 1, STREAM_DAWDLE = 2, STREAM_DEMAND = 3, STREAM_ROUTE = 4, STREAM_DEPARTPOS = 5 };
 
 // ---------------------------------------------------------------------------------------------
 // car-following primitives (SUMO Euler update, dt = 1 s) -- see DESIGN.md §4.2

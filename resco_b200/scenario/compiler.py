@@ -478,7 +478,8 @@ def compile_demand(arrays: Dict[str, np.ndarray], meta: Dict[str, object], idx: 
             continue
         lane_i = (m0 & -m0).bit_length() - 1      # lowest-index usable lane ("best"-lane insertion)
         origin_lane = int(a["edge_lane0"][edges[0]]) + lane_i
-        rows.append((origin_lane, tr.depart - begin, file_index[fi], rid, vti, episode_of[fi], fi))
+        rows.append((origin_lane, tr.depart - begin, file_index[fi], rid, vti, episode_of[fi], fi,
+                     1 if tr.depart_pos == "random_free" else 0))
     rows.sort(key=lambda r: (r[5], r[0], r[1], r[2]))
     origins = sorted({r[0] for r in rows})
     o_index = {o: i for i, o in enumerate(origins)}
@@ -503,6 +504,8 @@ def compile_demand(arrays: Dict[str, np.ndarray], meta: Dict[str, object], idx: 
         trip_file=np.array([r[2] for r in rows], np.int32).reshape(-1),
         trip_route=np.array([r[3] for r in rows], np.int32).reshape(-1),
         trip_vtype=np.array([r[4] for r in rows], np.int32).reshape(-1),
+        # <vehicle departPos="random_free"> (arterial4x4 route files): 1, else 0 (departPos="base")
+        trip_depart_pos=np.array([r[7] for r in rows], np.int32).reshape(-1),
     )
     if R > 1:
         out["bank_origin_off"] = bank

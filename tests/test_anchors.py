@@ -36,6 +36,10 @@ BANDS = {
     # over the -201201945#* chain.  Whether SUMO does better at this spot cannot be checked here.  The band is a
     # regression guard around today's value, NOT an agreement claim.
     ("ingolstadt21", "FIXED"): (1.6, 2.2, "median", "open deviation: coupled signals 243641585/gneJ257"),
+    # The reference's 30 MAXWAVE episodes on arterial4x4 are skewed (median 711 s, mean 821 s, p90 1219 s, max 1258 s): the
+    # map is oversaturated (under half of the 2484 trips ever depart) and some episodes lock up.  Five seeds of this model
+    # with departPos="random_free" spread over 825 .. 1011 s; the median of three has to stay below the reference's p90.
+    ("arterial4x4", "MAXWAVE"): (0.70, 1.45, "median", "oversaturated map, skewed reference distribution"),
 }
 MAPS_FIXED = ["cologne1", "cologne3", "cologne8", "ingolstadt1", "ingolstadt7", "ingolstadt21"]
 MAPS_CTRL = ["cologne1", "cologne3", "cologne8", "ingolstadt1", "ingolstadt7", "grid4x4", "arterial4x4"]

@@ -332,7 +332,9 @@ def test_batched_states_from_the_kernel_match_dict_view(map_name, key, rkey):
 
 @pytest.mark.parametrize("map_name,tile,mode,policy", [("cologne8", 0, "gmem", "cyclic"), ("cologne8", 32, "redo", "maxpressure"),
                                                        ("cologne8", 32, "list", "maxpressure"), ("ingolstadt21", 256, "list", "cyclic"),
-                                                       ("grid4x4", 64, "redo+list", "maxpressure")])
+                                                       ("grid4x4", 64, "redo+list", "maxpressure"),
+                                                       ("arterial4x4", 0, "gmem", "cyclic"), ("arterial4x4", 32, "redo", "maxpressure"),
+                                                       ("arterial4x4", 32, "list", "maxpressure")])
 def test_store_larger_than_the_tile(map_name, tile, mode, policy, monkeypatch):
     """The vehicle store is not bounded by one CTA's shared memory, and results do not depend on the tile size.
     gmem: RESCO_B200_GMEM=1, the whole store lives in the per-CTA global-memory workspace (tile_buffers == 0).
@@ -342,10 +344,12 @@ def test_store_larger_than_the_tile(map_name, tile, mode, policy, monkeypatch):
           instance per CTA): instances go on the overflow list and through the overflow pass (global workspace).
     redo+list: grid4x4 with a 64-vehicle tile and synthetic demand above capacity (~2600 vehicles per instance): the
           in-CTA redo tile is outgrown too.
+    arterial4x4: the same three modes on the map whose vehicles depart at random free positions (departPos="random_free":
+          the newcomer takes a slot BETWEEN the vehicles of its lane, tests/test_depart_pos.py).
     Always the same kernel and bit-identical results, nothing refused."""
     if mode == "gmem":
         monkeypatch.setenv("RESCO_B200_GMEM", "1")
-    if mode == "list" and map_name == "cologne8":
+    if mode == "list" and map_name in ("cologne8", "arterial4x4"):
         monkeypatch.setenv("RESCO_B200_REDO", "0")
     n_env = 11
     kw = dict(tile_vcap=tile)
@@ -378,6 +382,25 @@ def test_store_larger_than_the_tile(map_name, tile, mode, policy, monkeypatch):
         assert deferred > 0, (redone, deferred, sg["n_active"])
     if mode != "gmem":
         assert sg["n_active"].max() > tile
+
+
+def test_random_free_departures_under_saturation():
+    """arterial4x4 for 1000 s under MAXPRESSURE: the map is oversaturated, so most of the ten random positions drawn per
+    departure are refused, vehicles are placed between others and the base-position fallback is taken too."""
+    n_env = 16
+    sc, m, g, o = _pair("arterial4x4", n_env)
+    assert sc.arrays["trip_depart_pos"].all()
+    g.observe(); o.observe()
+    for step in range(200):
+        act = util.maxpressure_actions(sc, m, o.obs()["mplight"])
+        g.env_step(act); o.env_step(act)
+        if step % 10 == 9:
+            util.assert_same_obs(g.obs(), o.obs(), f"step {step}")
+    for e in range(n_env):
+        util.assert_same_state(g, o, e, f"env {e}")
+    sg = g.stats()
+    util.assert_same_stats(sg, o.stats(), "arterial4x4")
+    assert (sg["n_cap_refused"] == 0).all() and (sg["anomalies"] == 0).all() and (sg["n_backlog"] > 0).any()
 
 
 def test_synthetic_sweep_top_rate_is_not_truncated():
