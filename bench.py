@@ -175,30 +175,83 @@ def cpu_baseline(key="c2", n_steps=120, n_inst=None, cores=None, warm=None):
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed regions: an NVML polling thread (2 ms period; a 20-step window of the
+    headline config lasts ~50 ms, too short for an `nvidia-smi -lms` child to report once), gated by window(): samples
+    are kept only while a timed region is open.  Falls back to the nvidia-smi child if NVML cannot be opened."""
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"),
+               (0x80, "hw_power_brake_slowdown"))
 
     def __init__(self, gpu_index):
-        self.rows = []
+        self.rows = []            # nvidia-smi fallback rows
+        self.sm, self.mask = [], 0
+        self.max_mhz = None
         self.proc = None
         self.gpu = gpu_index
+        self.open = False         # a timed region is running
+        self.alive = False
+        self.source = None
+
+    def _nvml_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [x for x in vis.split(",") if x.strip() != ""]
+        if ids and all(x.strip().isdigit() for x in ids) and self.gpu < len(ids):
+            return int(ids[self.gpu])
+        return self.gpu
 
     def start(self):
+        if self.alive or self.proc is not None:
+            return
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._nvml_index())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+
+            def poll():
+                while self.alive:
+                    if self.open:
+                        try:
+                            self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                            self.mask |= int(reasons(h))
+                        except Exception:
+                            pass
+                    time.sleep(0.002)
+            self.alive, self.source = True, "nvml"
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.alive = False
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi -lms 100 (whole run)"
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
+
+    def window(self, is_open):
+        self.open = bool(is_open)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.alive:
+            self.alive = False
+            self.thread.join(timeout=1)
+            return dict(sm_mhz=float(np.median(self.sm)) if self.sm else None,
+                        sm_min_mhz=float(np.min(self.sm)) if self.sm else None, sm_max_mhz=self.max_mhz,
+                        reasons=sorted(n for bit, n in self.REASONS if self.mask & bit), samples=len(self.sm),
+                        source="NVML polled every 2 ms inside the timed regions (device-timed steps and e2e steps)")
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         self.proc.terminate()
@@ -217,7 +270,7 @@ class ClockSampler:
                 if len(r) > col and r[col].lower().startswith("active"):
                     reasons.add(name)
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+                    reasons=sorted(reasons), samples=len(sm), source=self.source)
 
 
 def algorithmic_bytes_per_step(m, vbar, obs_floats_per_signal=13):
@@ -340,17 +393,18 @@ def run_ours(args):
                 preroll()
 
         preroll()
+        if rank == 0:
+            sampler.start()                     # (idempotent) the polling thread is up before the warm-up steps
         for _ in range(args.warmup):
             ensure_room(); one_step(); state["step"] += 1
         barrier()
         st0 = [s.stats() for s in sims]
-        if rank == 0 and rate == cfg["rates"][0]:
-            sampler.start()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         kern_ms, deferred, redone = [], 0, 0
         barrier()
         if args.profile:
             torch.cuda.profiler.start()         # ncu --profile-from-start off: captures start at the timed steps
+        sampler.window(True)
         wall0 = time.perf_counter()
         for i in range(args.steps):
             ensure_room()
@@ -371,6 +425,7 @@ def run_ours(args):
                 ti = sims[0].tile_info()
                 deferred, redone = max(deferred, ti["last_deferred"]), max(redone, ti["last_redone"])
         barrier()
+        sampler.window(False)
         if args.profile:
             torch.cuda.profiler.stop()
         wall = time.perf_counter() - wall0
@@ -394,7 +449,6 @@ def run_ours(args):
         if rate != cfg["rates"][-1]:
             for s in sims:
                 s.close()
-    clocks = sampler.stop() if rank == 0 else None
     sc, m, sims, streams, parts, vbar, kern_ms, S = last
     total_env = n_env * world
     value = total_env * tot_steps / (tot_ms / 1e3)
@@ -444,6 +498,7 @@ def run_ours(args):
                 h.env_step_host_async(hact[hi](obs_half[hi]), reward_kind=rk, stream=st)
             obs_half = [h.wait()[0] for h in halves]
         barrier()
+        sampler.window(True)
         t0 = time.perf_counter()
         for hi, (h, st) in enumerate(zip(halves, hstreams)):        # prime: one step in flight per half
             h.env_step_host_async(hact[hi](obs_half[hi]), reward_kind=rk, stream=st)
@@ -473,6 +528,7 @@ def run_ours(args):
         for _ in range(pipe_warm):
             mp_step()
         barrier()
+        sampler.window(True)
         t0 = time.perf_counter()
         for _ in range(pipe_steps):
             mp_step()
@@ -484,6 +540,8 @@ def run_ours(args):
                    mode="MPLight's shared policy runs on the device (rs_policy_frap), so a step's inputs never leave HBM; "
                         "per step: FRAP + fused env step per half-batch on 2 streams, D2H of the pressure reward into pinned "
                         "memory, L2 flush inside the timed region")
+    sampler.window(False)
+    clocks = sampler.stop() if rank == 0 else None
     te = torch.tensor([e2e_t], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
