@@ -1126,8 +1126,7 @@ static int launch_run(RsSim* s, const DevSim& d, size_t smem_per_instance, int r
 //  1024/(TPI*G) = 64 registers per thread)
 //  The shapes rs_create can choose (fit_group: 8, 7, 6, 5 instances of 64 threads, 4 of 128, 2 or 1 of 512); other
 //  combinations were measured in round 1 and are no longer compiled.
-#define RS_VARIANTS(X) X(64, 5, 1) X(64, 6, 1) X(64, 7, 1) X(64, 8, 1) X(128, 4, 1) X(512, 1, 1) X(512, 2, 1) X(512, 1, 2) \
-  X(64, 4, 2) X(64, 2, 4) /* experiments: several lock-step groups per SM (RESCO_B200_BLOCK / GROUP / MINB) */
+#define RS_VARIANTS(X) X(64, 5, 1) X(64, 6, 1) X(64, 7, 1) X(64, 8, 1) X(128, 4, 1) X(512, 1, 1) X(512, 2, 1) X(512, 1, 2)
 
 static int launch_variant(RsSim* s, int block, int group, int minb, const DevSim& d, size_t smem_per_instance, int resident,
                           int n_work, const RunArgs& a, cudaStream_t st) {
