@@ -42,7 +42,12 @@ struct FrapShared {
   float w[FP_TOTAL];
   float ph_part[2][16];   // lane_embedding over the phase half of its input (+ bias), for "movement in the phase" 0 / 1
   float rel[2][20];       // relation branch for competition-mask values 0 / 1 (mplight.py:116-119)
+  float lct[16][40];      // lane_conv.weight transposed: [input u][k]; k < 20: first half of the pair, else second half
+                          // (threads with consecutive k read consecutive words instead of one bank)
 };
+// row strides of the per-block scratch arrays, odd so that threads working on different rows / pairs hit different banks
+constexpr int kPdStride = 17;   // [R][12] movement embeddings of 16 floats
+constexpr int kFsStride = 41;   // [R][n_pairs] pair embeddings of 40 floats: first (20) | second (20)
 
 // obs: [rows][13] states.mplight (phase index, 12 pressures); pairs [n_pairs][2]; comp [n_pairs][n_pairs - 1] 0/1;
 // order [S][n_pairs][2] = (pair index, action) in the reference's evaluation order, -1 terminates (k_policy's table);
@@ -55,11 +60,15 @@ __global__ void __launch_bounds__(kFrapThreads) k_policy_frap(const float* __res
   extern __shared__ __align__(16) unsigned char fsm[];
   FrapShared& F = *reinterpret_cast<FrapShared*>(fsm);
   const int R = kFrapThreads / n_pairs;                 // rows per block
-  float* pd = reinterpret_cast<float*>(fsm + sizeof(FrapShared));        // [R][12][16]
-  float* fs = pd + R * 12 * 16;                                          // [R][n_pairs][40]: first (20) | second (20)
-  float* qs = fs + R * n_pairs * 40;                                     // [R][n_pairs]
+  float* pd = reinterpret_cast<float*>(fsm + sizeof(FrapShared));        // [R][12][kPdStride]
+  float* fs = pd + R * 12 * kPdStride;                                   // [R][n_pairs][kFsStride]
+  float* qs = fs + R * n_pairs * kFsStride;                              // [R][n_pairs]
   const int tid = threadIdx.x;
   for (int i = tid; i < FP_TOTAL; i += kFrapThreads) F.w[i] = __ldg(params + i);
+  for (int x = tid; x < 16 * 40; x += kFrapThreads) {
+    const int u = x / 40, k = x % 40;
+    F.lct[u][k] = __ldg(params + FP_LCW + (k < 20 ? k : k - 20) * 32 + (k < 20 ? 0 : 16) + u);
+  }
   __syncthreads();
   if (tid < 32) {
     const int e = tid >> 4, u = tid & 15;
@@ -90,26 +99,25 @@ __global__ void __launch_bounds__(kFrapThreads) k_policy_frap(const float* __res
         acc = __fmaf_rn(F.w[FP_LEW + u * 8 + 4 + c], sigmoidf_(__fmaf_rn(F.w[FP_DW + c], xm, F.w[FP_DB + c])), acc);
       v = fmaxf(acc, 0.0f);
     }
-    pd[x] = v;
+    pd[(r * 12 + m) * kPdStride + u] = v;
   }
   __syncthreads();
   // ---- B: pair embeddings through the two halves of the 1x1 lane convolution ----
   for (int x = tid; x < R * n_pairs * 40; x += kFrapThreads) {
     const int r = x / (n_pairs * 40), i = (x / 40) % n_pairs, k = x % 40;
-    const float* pa = pd + (r * 12 + __ldg(pairs + 2 * i)) * 16;
-    const float* pb = pd + (r * 12 + __ldg(pairs + 2 * i + 1)) * 16;
-    const int kk = k < 20 ? k : k - 20;
-    const float* wrow = F.w + FP_LCW + kk * 32 + (k < 20 ? 0 : 16);
-    float acc = k < 20 ? F.w[FP_LCB + kk] : 0.0f;
-    for (int u = 0; u < 16; ++u) acc = __fmaf_rn(wrow[u], pa[u] + pb[u], acc);
-    fs[x] = acc;
+    const float* pa = pd + (r * 12 + __ldg(pairs + 2 * i)) * kPdStride;
+    const float* pb = pd + (r * 12 + __ldg(pairs + 2 * i + 1)) * kPdStride;
+    float acc = k < 20 ? F.w[FP_LCB + k] : 0.0f;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) acc = __fmaf_rn(F.lct[u][k], pa[u] + pb[u], acc);
+    fs[(r * n_pairs + i) * kFsStride + k] = acc;
   }
   __syncthreads();
   // ---- C: pair competition: one thread per (row, pair i), the n - 1 opponents three at a time so that every weight of
   //      the 20 x 20 layer (one 128-bit shared-memory broadcast load per four) feeds three FMAs ----
   const int r = tid / n_pairs, i = tid % n_pairs;
   if (r < R) {
-    const float* first = fs + (r * n_pairs + i) * 40;
+    const float* first = fs + (r * n_pairs + i) * kFsStride;
     float f[20];
 #pragma unroll
     for (int k = 0; k < 20; ++k) f[k] = first[k];
@@ -123,7 +131,7 @@ __global__ void __launch_bounds__(kFrapThreads) k_policy_frap(const float* __res
         live[t] = jj + t < n_opp;
         const int jo = live[t] ? jj + t : jj;                       // a dead slot repeats a live one, its result is dropped
         const int j = jo < i ? jo : jo + 1;                         // the jo-th OTHER pair, in the reference's order
-        const float* sj = fs + (r * n_pairs + j) * 40 + 20;
+        const float* sj = fs + (r * n_pairs + j) * kFsStride + 20;
         const float* rl = F.rel[__ldg(comp + i * n_opp + jo)];
 #pragma unroll
         for (int k = 0; k < 20; ++k) c[t][k] = fmaxf(f[k] + sj[k], 0.0f) * rl[k];
@@ -171,7 +179,7 @@ __global__ void __launch_bounds__(kFrapThreads) k_policy_frap(const float* __res
 
 inline size_t frap_smem_bytes(int n_pairs) {
   const int R = kFrapThreads / n_pairs;
-  return sizeof(FrapShared) + sizeof(float) * ((size_t)R * 12 * 16 + (size_t)R * n_pairs * 40 + (size_t)R * n_pairs);
+  return sizeof(FrapShared) + sizeof(float) * ((size_t)R * 12 * kPdStride + (size_t)R * n_pairs * kFsStride + (size_t)R * n_pairs);
 }
 
 // uniform random green phase: Philox keyed by (seed, global instance id, signal, instance tick)
