@@ -84,19 +84,25 @@ __global__ void __launch_bounds__(kFrapThreads) k_policy_frap(const float* __res
   __syncthreads();
   const int row0 = blockIdx.x * R;
   // ---- A: per movement: relu(lane_embedding(cat(sigmoid(p[in phase]), sigmoid(d(x))))) ----
+  // the four sigmoid(d(x)) of a movement once (scratch: the pair-embedding array, not yet in use), then the 16 outputs
+  float* sg = fs;                                                        // [R][12][4]
+  for (int x = tid; x < R * 12 * 4; x += kFrapThreads) {
+    const int r = x / 48, m = (x >> 2) % 12, c = x & 3;
+    const int row = row0 + r;
+    sg[x] = row < rows ? sigmoidf_(__fmaf_rn(F.w[FP_DW + c], __ldg(obs + (size_t)row * 13 + 1 + m), F.w[FP_DB + c])) : 0.0f;
+  }
+  __syncthreads();
   for (int x = tid; x < R * 12 * 16; x += kFrapThreads) {
     const int r = x / 192, m = (x / 16) % 12, u = x & 15;
     const int row = row0 + r;
     float v = 0.0f;
     if (row < rows) {
-      const float* ob = obs + (size_t)row * 13;
-      const int act = (int)__ldg(ob);
+      const int act = (int)__ldg(obs + (size_t)row * 13);
       int e = 0;
       if (act >= 0 && act < n_pairs) e = (m == __ldg(pairs + 2 * act) || m == __ldg(pairs + 2 * act + 1)) ? 1 : 0;
-      const float xm = __ldg(ob + 1 + m);
       float acc = F.ph_part[e][u];
-      for (int c = 0; c < 4; ++c)
-        acc = __fmaf_rn(F.w[FP_LEW + u * 8 + 4 + c], sigmoidf_(__fmaf_rn(F.w[FP_DW + c], xm, F.w[FP_DB + c])), acc);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc = __fmaf_rn(F.w[FP_LEW + u * 8 + 4 + c], sg[(r * 12 + m) * 4 + c], acc);
       v = fmaxf(acc, 0.0f);
     }
     pd[(r * 12 + m) * kPdStride + u] = v;
