@@ -28,7 +28,8 @@ _LIB = None
 def build_library(force: bool = False, verbose: bool = False) -> str:
     """Compile the CUDA extension in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     srcs = [os.path.join(_CSRC, "sim.cu")]
-    deps = srcs + [os.path.join(_CSRC, "sim_kernels.cuh"), os.path.join(_HERE, "..", "include", "resco_b200.h")]
+    deps = srcs + [os.path.join(_CSRC, "sim_kernels.cuh"), os.path.join(_CSRC, "agents.cuh"),
+                   os.path.join(_HERE, "..", "include", "resco_b200.h")]
     if (not force and os.path.exists(LIB_PATH)
             and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(d) for d in deps)):
         return LIB_PATH
